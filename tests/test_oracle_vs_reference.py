@@ -1,0 +1,66 @@
+"""Pins oracle/assembly_oracle.c against the UNMODIFIED reference (real AssemblySwarmEnv driving its
+own AssemblyEnv.cpp, compiled by oracle/Makefile into oracle/_ref/).  Bit-exact on every output of
+every step.  Build-container only: skipped where /root/reference is not mounted (GPU box)."""
+import numpy as np
+import pytest
+
+from oracle import live_reference as lr
+from oracle import oracle as orc
+from tests.helpers import goal_seeking_action
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not lr.available(), reason="reference checkout / oracle/_ref not available")]
+
+FIELDS = ("p", "dp", "obs", "rew", "prior", "nbr", "inf", "sen", "occ")
+
+
+def rollout_pair(n_a, seed, mode, steps):
+    env = lr.make_env(n_a)
+    np.random.seed(seed)
+    env.reset()
+    e = env.env
+    P = orc.make_params(n_a, e.n_g, float(e.l_cell), float(e.r_avoid))
+    ob = orc.OracleBatch([P])
+    ob.p[0], ob.dp[0] = e.p, e.dp
+    ob.set_grid(0, e.grid_center)
+    ob.observe()
+    assert np.array_equal(ob.obs[0], e.obs)
+    assert np.array_equal(ob.neighbor_index[0], e.neighbor_index)
+    assert np.array_equal(ob.sensed_index[0], e.sensed_index)
+    rng = np.random.RandomState(seed + 1)
+    stats = dict(in_shape=0, subsampled=0, occupied=0, reward=0.0)
+    for t in range(steps):
+        if mode == "random":
+            a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32)
+        else:
+            a = goal_seeking_action(e.obs, e.dp, rng)
+        obs, rew, done, info, prior = env.step(a)
+        ob.step(a[None])
+        got = dict(p=ob.p[0], dp=ob.dp[0], obs=ob.obs[0], rew=ob.reward[0], prior=ob.a_prior[0],
+                   nbr=ob.neighbor_index[0], inf=ob.in_flags[0], sen=ob.sensed_index[0], occ=ob.occupied_index[0])
+        ref = dict(p=e.p, dp=e.dp, obs=obs, rew=rew, prior=prior, nbr=e.neighbor_index, inf=e.in_flags,
+                   sen=e.sensed_index, occ=e.occupied_index)
+        for k in FIELDS:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), f"{k} differs at step {t} (n_a={n_a}, seed={seed}, {mode})"
+        assert not done.any()
+        stats["in_shape"] += int(e.in_flags.sum())
+        stats["occupied"] += int((e.occupied_index >= 0).sum())
+        stats["subsampled"] += int(((e.sensed_index >= 0).sum(1) == 80).sum())
+        stats["reward"] += float(rew.sum())
+    return stats
+
+
+@pytest.mark.parametrize("seed", [226, 1, 2])
+def test_random_actions_30_agents_200_steps(seed):
+    rollout_pair(30, seed, "random", 200)
+
+
+@pytest.mark.parametrize("seed", [226, 3])
+def test_goal_seeking_exercises_in_shape_branches(seed):
+    st = rollout_pair(30, seed, "goal", 200)
+    assert st["in_shape"] > 500 and st["subsampled"] >= 1 and st["occupied"] > 1000 and st["reward"] > 0, st
+
+
+@pytest.mark.parametrize("n_a,steps", [(1, 20), (2, 50), (10, 100), (64, 60), (200, 10)])
+def test_other_swarm_sizes(n_a, steps):
+    rollout_pair(n_a, 11 + n_a, "goal", steps)
