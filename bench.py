@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the assembly-env step() hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's fused sm_100a kernel
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path, all host cores
+
+A "step" = one env.step() of every env of the batch: 30 agents x 65 536 envs per GPU (BASELINE config 3; at N=1
+it is the single-GPU instance of the configuration the metric is quoted on).  Envs are independent, so N GPUs run N
+shards with no data-path collective ("weak" scaling: per-GPU work is fixed); the only exchange is the max-over-ranks
+of the elapsed time.  One JSON line is printed by rank 0.
+
+    value     device-resident throughput: actions already in HBM, CUDA events around exactly K steps
+    e2e       same metric through the host-buffer C-ABI call (swarm_step_host): pinned host actions H2D, step,
+              obs + reward + a_prior D2H, every step, inside the timed region
+    roofline  algorithmic bytes per launch / mean launch duration vs the measured HBM copy peak
+    cpu_baseline  the reference's C++ (oracle/_ref) + NumPy glue timed on this box's host cores (rank 0, N=1)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+METRIC = "agent_steps_per_sec"
+UNIT = "agent-steps/s"
+
+
+def load_shapes():
+    z = np.load(os.path.join(REPO, "tests", "golden", "shapes.npz"))
+    n_g = z["n_g"]
+    return dict(l_cell=z["l_cell"].copy(), n_g=n_g.copy(),
+                grid_origin=[np.ascontiguousarray(z["grid_coords"][k, :n_g[k]].T) for k in range(len(n_g))])
+
+
+def synth_batch(E, n_a, shapes, seed, regime):
+    """Vectorised domain randomisation in the spirit of assembly.py:156-223 (shape, rotation, offset, initial p/dp).
+    regime 'random': the reference's reset distribution.  'converged': agents start on cells of their shape so the
+    in-shape / occupancy / subsample / reward branches are the common case."""
+    rng = np.random.RandomState(seed)
+    S = len(shapes["l_cell"])
+    ngm = int(shapes["n_g"].max())
+    k = rng.randint(0, S, E)
+    ang = np.pi * rng.uniform(-1, 1, E)
+    off = rng.uniform(-1.4, 1.4, (E, 2))
+    blocks = np.zeros((E, 2 * ngm))
+    n_g = shapes["n_g"][k].astype(np.int32)
+    l_cell = shapes["l_cell"][k]
+    c, s = np.cos(ang), np.sin(ang)
+    p = np.empty((E, 2, n_a))
+    for sid in range(S):
+        sel = np.nonzero(k == sid)[0]
+        if sel.size == 0:
+            continue
+        g = shapes["grid_origin"][sid]                         # [2, ng]
+        ng = g.shape[1]
+        gx = c[sel, None] * g[0][None] + s[sel, None] * g[1][None] + off[sel, 0:1]
+        gy = -s[sel, None] * g[0][None] + c[sel, None] * g[1][None] + off[sel, 1:2]
+        blocks[sel, :ng] = gx
+        blocks[sel, ng:2 * ng] = gy
+        if regime == "converged":
+            pick = np.stack([rng.choice(ng, n_a, replace=False) for _ in sel])
+            p[sel, 0] = np.take_along_axis(gx, pick, 1) + rng.normal(0, 0.01, pick.shape)
+            p[sel, 1] = np.take_along_axis(gy, pick, 1) + rng.normal(0, 0.01, pick.shape)
+    if regime != "converged":
+        wide = rng.uniform(-1, 1, E) > 0
+        p_wide = rng.uniform(-2.4, 2.4, (E, 2, n_a))
+        p_clu = rng.uniform(-1, 1, (E, 2, n_a)) + rng.uniform(-1.4, 1.4, (E, 2, 1))
+        p = np.where(wide[:, None, None], p_wide, p_clu)
+        dp = rng.uniform(-0.5, 0.5, (E, 2, n_a))
+    else:
+        dp = rng.uniform(-0.05, 0.05, (E, 2, n_a))
+    return blocks, n_g, l_cell, p, dp
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_hbm_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ref_glue
+    shapes = load_shapes()
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.ref_procs or cores))
+    if not ref_glue.available():
+        # the reference C++ was not compiled here: fall back to the C port of it (never to the product)
+        from oracle import oracle as orc
+        t0 = time.perf_counter()
+        res = port_rollouts(orc, shapes, args.n_a, procs, args.ref_envs, args.ref_steps)
+        kind, sample = "port", f"{res['envs']} envs x {args.ref_steps} steps, oracle C port, {procs} OpenMP threads"
+        value, secs = res["value"], time.perf_counter() - t0
+    else:
+        episodes = min(max(1, (args.steps + 1) // 2), 100)   # a "step" of this arm = 100 env.step() calls per process (bounded sample)
+        for _ in range(max(0, min(args.warmup, 1))):
+            ref_glue.timed_rollouts(args.n_a, shapes, procs, 1, 20)
+        res = ref_glue.timed_rollouts(args.n_a, shapes, procs, episodes, args.ref_steps)
+        kind = "reference"
+        sample = (f"{procs} processes x {episodes} episodes x {args.ref_steps} steps x {args.n_a} agents, one env each "
+                  f"(reference AssemblyEnv.cpp via oracle/_ref + its NumPy glue), env.step() time only")
+        value, secs = res["value"], res["seconds"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"assembly env, {args.n_a} agents, reference CPU path (single env per process; the reference has no vector env)",
+                   "n_a": args.n_a, "processes": procs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def port_rollouts(orc, shapes, n_a, threads, envs, steps):
+    r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    blocks, n_g, l_cell, p, dp = synth_batch(envs, n_a, shapes, 226, "random")
+    params = [orc.make_params(n_a, int(n_g[e]), float(l_cell[e]), r_avoid) for e in range(envs)]
+    ob = orc.OracleBatch(params, nthreads=threads, ng_max=int(shapes["n_g"].max()))
+    ob.grid[:] = 0
+    for e in range(envs):
+        ob.grid[e, :2 * n_g[e]] = blocks[e, :2 * n_g[e]]
+    ob.p[:], ob.dp[:] = p, dp
+    ob.observe()
+    acts = [orc.fill_actions(envs, n_a, 226, t) for t in range(steps)]
+    t0 = time.perf_counter()
+    for t in range(steps):
+        ob.step(acts[t])
+    dt = time.perf_counter() - t0
+    return dict(value=envs * steps * n_a / dt, envs=envs, seconds=dt)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--n-a", dest="n_a", type=int, default=30)
+    ap.add_argument("--layout", default="production", choices=["production", "parity"],
+                    help="production: fp64 state, fp32 obs/reward/prior; parity: everything fp64 + index arrays")
+    ap.add_argument("--regime", default="random", choices=["random", "converged"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-steps", type=int, default=200)
+    ap.add_argument("--ref-envs", type=int, default=256)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from marl_llm_b200.batched import BatchedAssemblySim, r_avoid_for
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: the simulator has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    shapes = load_shapes()
+    E, n_a = args.envs_per_gpu, args.n_a
+    ngm = int(shapes["n_g"].max())
+    r_avoid = r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    parity = args.layout == "parity"
+    sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, device=local_rank,
+                             out_dtype=torch.float64 if parity else torch.float32, emit_indices=parity)
+    blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, args.regime)   # shard = own seed = own envs
+    sim.set_grid(blocks, n_g, l_cell)
+    sim.set_state(p, dp)
+    sim.observe()
+
+    K, W = args.steps, args.warmup
+    ring = min(K + W, 16)
+    acts = torch.empty(ring, E, 2, n_a, dtype=torch.float32, device="cuda")
+    for r in range(ring):
+        sim.fill_actions(acts[r], seed=226, step=r, env_offset=rank * E)
+    torch.cuda.synchronize()
+
+    for t in range(W):
+        sim.step(acts[t % ring])
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(K):
+        sim.step(acts[(W + t) % ring])
+    ev1.record()
+    barrier()
+    launches = sim.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * E * n_a * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel ----
+    bytes_per_agent = sim.algorithmic_bytes_per_agent_step()
+    bytes_per_launch = bytes_per_agent * E * n_a
+    launch_ms = ms / K
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    peak, peak_src = measured_hbm_peak()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "swarm::k_step", "launch_ms": launch_ms,
+                "algorithmic_bytes_per_agent_step": bytes_per_agent}
+    prof = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.isfile(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(f"{args.layout}_{args.regime}_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        osz = 8 if parity else 4
+        act_h = torch.empty(ring, E, 2, n_a, dtype=torch.float32).pin_memory()
+        act_h.copy_(acts.cpu())
+        obs_h = torch.empty(E, sim.obs_dim, n_a, dtype=sim.out_dtype).pin_memory()
+        rew_h = torch.empty(E, 1, n_a, dtype=sim.out_dtype).pin_memory()
+        pri_h = torch.empty(E, 2, n_a, dtype=sim.out_dtype).pin_memory()
+        for t in range(min(W, 3)):
+            sim.step_host(act_h[t % ring], obs_h, rew_h, pri_h)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(K):
+            sim.step_host(act_h[(W + t) % ring], obs_h, rew_h, pri_h)
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ems], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ems = float(tms.item())
+        e2e = {"value": world * E * n_a * K / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": E * 2 * n_a * 4, "d2h_bytes_per_step": E * n_a * (sim.obs_dim + 1 + 2) * osz,
+               "ms_per_step": ems / K, "api": "swarm_step_host (C ABI, pinned host buffers)"}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_glue
+        cores = os.cpu_count() or 1
+        if ref_glue.available():
+            r = ref_glue.timed_rollouts(n_a, shapes, cores, 2, 200)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"{cores} processes x 2 episodes x 200 steps x {n_a} agents (reference C++ via oracle/_ref + NumPy glue)"}
+        else:
+            from oracle import oracle as orc
+            r = port_rollouts(orc, shapes, n_a, cores, 64 * cores, 50)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{r['envs']} envs x 50 steps, oracle C port, {cores} OpenMP threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"assembly env, {n_a} agents x {E} envs per GPU, env-sharded (BASELINE config 3)",
+                       "n_a": n_a, "envs_per_gpu": E, "layout": args.layout, "regime": args.regime,
+                       "out_dtype": "f64" if parity else "f32", "state_dtype": "f64",
+                       "l2": f"working set per step {bytes_per_launch / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
+                       "actions": f"ring of {ring} pre-generated device buffers"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+/*
+ * swarm_b200.h — C ABI of the B200-native batched simulator for the MARL-LLM assembly env step path.
+ *
+ * One shared library (marl_llm_b200/lib/libswarm_b200.so, also reachable as libAssemblyEnv.so)
+ * exports two groups of entry points, all `extern "C"`, plain pointers and sizes only:
+ *
+ *  (1) LEGACY, stateless, HOST pointers — the five symbols the reference Python env binds with ctypes
+ *      (cus_gym/gym/envs/customized_envs/envs_cplus/c_lib.py:11-22 loads build/libAssemblyEnv.so;
+ *      assembly.py:234-255, 357-380, 460-466, 495-504, 613-624 call them).  Same names, argument order,
+ *      layouts, in-place output convention and `void` return as AssemblyEnv.h:13-58,64-81,98-109, so the
+ *      reference's assembly.py runs unchanged on top of this library.  Each call copies its inputs to the
+ *      GPU, runs the corresponding sm_100a kernel for a batch of one env, and copies the outputs back.
+ *
+ *  (2) BATCHED, handle based, DEVICE-resident — the product path: E independent envs stepped by ONE fused
+ *      kernel launch per step (forces + walls + integrator + k-NN + grid scan + occupancy + observation
+ *      packing + reward + next prior).  Not in the reference (it has no vector env); per-env
+ *      layouts are identical to the reference's so that obs[e] == the reference's obs for that env.
+ *
+ * Reference abbreviations used below:
+ *   HDR = cus_gym/gym/envs/customized_envs/envs_cplus/src/AssemblyEnv.h
+ *   CPP = cus_gym/gym/envs/customized_envs/envs_cplus/src/AssemblyEnv.cpp
+ *   ENV = cus_gym/gym/envs/customized_envs/assembly.py
+ */
+#ifndef SWARM_B200_H
+#define SWARM_B200_H
+
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ============================================================================================
+ * (1) Legacy entry points (HOST pointers, stateless).  A CUDA failure inside one of these cannot be
+ *     reported through the reference's void signatures: it is printed to stderr and the process aborts
+ *     (there is deliberately NO CPU fallback).
+ * ============================================================================================ */
+
+/* replaces HDR:13-34 / CPP:18-351; bound at ENV:234-255.
+ * p, dp, heading: [dim][n_a] f64; obs: [obs_dim_agent][n_a] f64 (out); boundary_pos: [4] = xmin,ymax,xmax,ymin;
+ * grid_center: [dim][n_g] f64; neighbor_index: [n_a][topo_nei_max] i32 (out); in_flags: [n_a] i32 (out);
+ * sensed_index: [n_a][num_obs_grid_max] i32 (out); occupied_index: [n_a][num_occupied_grid_max] i32 (out);
+ * condition: bool[4] = is_periodic, is_Cartesian, is_con_self_state, is_feature_norm (the last is never read
+ * by the reference either, CPP:80,88,103,294).  All outputs are fully written (the caller's -1 / 0 pre-fill
+ * of ENV:227-231 is not relied upon). */
+void _get_observation(double *p, double *dp, double *heading, double *obs, double *boundary_pos,
+                      double *grid_center, int *neighbor_index, int *in_flags, int *sensed_index,
+                      int *occupied_index, double d_sen, double r_avoid, double l_cell, double Vel_max,
+                      int topo_nei_max, int num_obs_grid_max, int num_occupied_grid_max, int n_a, int n_g,
+                      int obs_dim_agent, int dim, bool *condition);
+
+/* replaces HDR:35-58 / CPP:354-626; bound at ENV:357-380.  reward: [1][n_a] f64 (out).
+ * condition: bool[5] = is_periodic, is_Cartesian, penalize_entering, penalize_interaction, penalize_exploration.
+ * act, heading, occupied_index, is_collide_b2b, is_collide_b2w, coefficients are accepted and ignored exactly as
+ * the live branch of the reference ignores them (CPP:452-559). */
+void _get_reward(double *p, double *dp, double *heading, double *act, double *reward, double *boundary_pos,
+                 double *grid_center, int *neighbor_index, int *in_flags, int *sensed_index, int *occupied_index,
+                 double d_sen, double r_avoid, double l_cell, int topo_nei_max, int num_obs_grid_max,
+                 int num_occupied_grid_max, int n_a, int n_g, int dim, bool *condition, bool *is_collide_b2b,
+                 bool *is_collide_b2w, double *coefficients);
+
+/* replaces HDR:64-73 / CPP:735-815; bound at ENV:495-504.  sf_b2b: [dim][n_a] f64 (out);
+ * d_b2b_edge, d_b2b_center: [n_a][n_a] f64 and is_collide_b2b: [n_a][n_a] bool, as produced by ENV:442-457. */
+void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide_b2b, double *boundary_pos,
+                 double *d_b2b_center, int n_a, int dim, double k_ball, bool is_periodic);
+
+/* replaces HDR:75-81 / CPP:817-855; bound at ENV:460-466.  r: [n_a]; d_b2w: [4][n_a] f64 (out);
+ * isCollision: [4][n_a] bool (out). */
+void _get_dist_b2w(double *p, double *r, double *d_b2w, bool *isCollision, int dim, int n_a, double *boundary_pos);
+
+/* replaces HDR:98-109 / CPP:1061-1196; bound at ENV:613-624.  a_prior: [dim][n_a] f64 (out). */
+void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_center, int *neighbor_index,
+                          double d_sen, double r_avoid, double l_cell, int topo_nei_max, int n_a, int n_g, int dim);
+
+/* ============================================================================================
+ * (2) Batched, device-resident simulator.
+ * ============================================================================================ */
+
+typedef struct swarm_sim swarm_sim;   /* opaque */
+
+enum {
+    SWARM_OK = 0,
+    SWARM_ERR_INVALID = 1,       /* bad argument / inconsistent sizes                      */
+    SWARM_ERR_UNSUPPORTED = 2,   /* valid in the reference but outside this build's limits  */
+    SWARM_ERR_CUDA = 3,          /* a CUDA call failed; see swarm_last_error()              */
+    SWARM_ERR_NO_DEVICE = 4      /* no usable sm_100 device: there is no CPU fallback       */
+};
+
+enum { SWARM_F64 = 0, SWARM_F32 = 1 };
+
+/* Everything ENV:27-81,93-138,193-199 fixes per env class; per-env quantities (n_g, l_cell, grid) are set
+ * with swarm_set_grid(). */
+typedef struct swarm_config {
+    int32_t struct_size;            /* sizeof(swarm_config), ABI check                                 */
+    int32_t device;                 /* CUDA device ordinal                                             */
+    int32_t num_envs;               /* E                                                               */
+    int32_t n_a;                    /* agents per env (<= 1024)                       ENV:93           */
+    int32_t n_g_max;                /* capacity in cells per env (any n_g <= n_g_max)  ENV:179          */
+    int32_t topo_nei_max;           /* must be 6                                       ENV:34           */
+    int32_t num_obs_grid_max;       /* 80                                              ENV:128          */
+    int32_t num_occupied_grid_max;  /* 200                                             ENV:130          */
+    int32_t is_con_self_state;      /* obs_dim 192 (1) or 188 (0)                      ENV:107,801      */
+    int32_t is_periodic;            /* 0 only (is_boundary=True, the default)          ENV:99-103       */
+    int32_t want_prior;             /* training_method == 'llm_rl'                     ENV:605          */
+    int32_t out_dtype;              /* SWARM_F64 (reference dtype) or SWARM_F32 for obs/reward/a_prior  */
+    int32_t emit_indices;           /* also write sensed_index / occupied_index every step             */
+    int32_t exact_occupancy;        /* debug: always take the per-agent sequential occupancy filter    */
+    double d_sen;                   /* 0.4                                             ENV:199          */
+    double r_avoid;                 /*                                                 ENV:124          */
+    double size_a;                  /* 0.035                                           ENV:44           */
+    double k_ball, k_wall, c_wall;  /* 30, 100, 5                                      ENV:71,73,74     */
+    double dt, vel_max, mass;       /* 0.1, 0.8, 1                                     ENV:79,52,40     */
+    double boundary_pos[4];         /* xmin, ymax, xmax, ymin                          ENV:193-196      */
+} swarm_config;
+
+/* Device buffers owned by the CALLER (e.g. torch tensors); every pointer is a device pointer on
+ * `config.device` and must stay valid for the life of the handle.  OUT = f64 or f32 per out_dtype. */
+typedef struct swarm_buffers {
+    int32_t struct_size;
+    int32_t pad_;
+    double *p;                 /* [E][2][n_a]            in/out   ENV:203-208 */
+    double *dp;                /* [E][2][n_a]            in/out   ENV:215     */
+    double *grid;              /* [E][n_g_pad][2]        internal cell-major copy of grid_center, written by
+                                  swarm_set_grid; n_g_pad = swarm_grid_pad(n_g_max)                      */
+    int32_t *n_g;              /* [E]                    written by swarm_set_grid                         */
+    double *in_thresh;         /* [E]                    written by swarm_set_grid (in-shape threshold)    */
+    void *obs;                 /* [E][obs_dim][n_a] OUT  ENV:227, layout CPP:324-328                       */
+    void *reward;              /* [E][1][n_a]       OUT  ENV:353                                           */
+    void *a_prior[2];          /* 2 x [E][2][n_a]   OUT  ENV:612; double-buffered, see swarm_a_prior_ptr   */
+    int32_t *neighbor_index;   /* [E][n_a][6]            ENV:228                                           */
+    int32_t *in_flags;         /* [E][n_a]               ENV:229                                           */
+    int32_t *nearest_cell;     /* [E][n_a]               index of the nearest cell (CPP:884-885)           */
+    int32_t *sensed_index;     /* [E][n_a][80]           ENV:230   (may be NULL unless emit_indices)       */
+    int32_t *occupied_index;   /* [E][n_a][200]          ENV:231   (may be NULL unless emit_indices)       */
+} swarm_buffers;
+
+/* cells per env rounded up to the kernel's tile (multiple of 32) */
+int32_t swarm_grid_pad(int32_t n_g_max);
+/* 2*2*(6+1+self)+2*80, ENV:801 */
+int32_t swarm_obs_dim(const swarm_config *cfg);
+
+int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **out);
+int swarm_destroy(swarm_sim *sim);
+
+/* Upload target shapes for envs [env0, env0+count).  grid: per env a block of 2*n_g_max doubles whose first
+ * 2*n_g[e] hold the reference's grid_center[2][n_g] (ENV:187) — host pointer unless grid_on_device != 0.
+ * n_g, l_cell: host arrays [count] (ENV:163,179).  Invalidates the cached prior (like eval_assembly.py:34-57
+ * poking env.grid_center between steps). */
+int swarm_set_grid(swarm_sim *sim, int32_t env0, int32_t count, const double *grid, int grid_on_device,
+                   const int32_t *n_g, const double *l_cell, void *stream);
+
+/* Tell the handle that the caller overwrote p / dp (device buffers) outside step(): the next step recomputes the
+ * prior from the new state and the stale neighbor_index, exactly like the reference would (ENV:613-624). */
+int swarm_mark_state_dirty(swarm_sim *sim);
+
+/* reset() tail, ENV:221 -> _get_obs: observation (+ reward) of the current state, no dynamics. */
+int swarm_observe(swarm_sim *sim, void *stream);
+
+/* env.step(a), ENV:487-666 (agent_strategy 'input', Cartesian).  act: DEVICE [E][2][n_a], f32 or f64. */
+int swarm_step(swarm_sim *sim, const void *act, int act_dtype, void *stream);
+
+/* Same step through HOST buffers (pinned or pageable): H2D act, step, D2H obs / reward / a_prior (NULL = skip),
+ * synchronises the stream before returning.  This is the call a host-side caller of the reference would make. */
+int swarm_step_host(swarm_sim *sim, const float *act_host, void *obs_host, void *reward_host, void *a_prior_host,
+                    void *stream);
+
+/* a_prior returned by the most recent swarm_step (the reference's 5th return value, ENV:666). */
+void *swarm_a_prior_ptr(swarm_sim *sim);
+
+/* Synthetic actions U(-1,1) f32 [E][2][n_a] from a counter-based generator keyed by (seed, step, env_offset+e, k);
+ * bit-identical to oracle/assembly_oracle.c:orc_fill_actions.  Benchmark / test input only. */
+int swarm_fill_actions(swarm_sim *sim, uint64_t seed, uint64_t step, uint64_t env_offset, float *act_dev, void *stream);
+
+/* number of kernels this handle has launched so far */
+int64_t swarm_launch_count(const swarm_sim *sim);
+/* dynamic shared memory bytes and threads per CTA of the fused step kernel for this handle */
+int swarm_kernel_geometry(const swarm_sim *sim, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *ctas);
+
+/* Host-only helper (no GPU needed), exposed for tests: the double T with  sqrt(s) < d  <=>  s < T  (le == 0), or the
+ * double U with  sqrt(s) <= d  <=>  s <= U  (le != 0), sqrt being IEEE round-to-nearest.  The kernels compare squared
+ * distances with these instead of taking square roots. */
+double swarm_sqrt_threshold(double d, int le);
+
+const char *swarm_last_error(void);
+int swarm_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWARM_B200_H */

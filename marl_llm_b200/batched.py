@@ -1,0 +1,233 @@
+"""Device-resident batch of assembly environments stepped by the fused sm_100a kernel.
+
+Host side of the batched C ABI (include/swarm_b200.h, group 2).  torch is used for what the task statement
+says it is for: device memory (the state / output tensors below are plain torch tensors whose data_ptr()s are
+handed to the library once) and streams.  All arithmetic happens in marl_llm_b200/csrc.
+
+Per-env layouts equal the reference's (cus_gym/gym/envs/customized_envs/assembly.py):
+    p, dp            [E, 2, n_a]        float64      assembly.py:203-215
+    obs              [E, obs_dim, n_a]  out dtype    assembly.py:227,  AssemblyEnv.cpp:324-328
+    reward           [E, 1, n_a]        out dtype    assembly.py:353
+    done             [E, 1, n_a]        bool, always False (assembly.py:480-482)
+    a_prior          [E, 2, n_a]        out dtype    assembly.py:612
+    neighbor_index   [E, n_a, 6]  in_flags [E, n_a]  sensed_index [E, n_a, 80]  occupied_index [E, n_a, 200]  int32
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SwarmBuffers, SwarmConfig, SwarmError, check
+
+TOPO_NEI_MAX = 6          # assembly.py:34
+NUM_OBS_GRID_MAX = 80     # assembly.py:128
+NUM_OCC_GRID_MAX = 200    # assembly.py:130
+
+
+def r_avoid_for(n_a, n_gs, l_cells):
+    """assembly.py:124"""
+    return round(float(np.sqrt(4 * np.min(n_gs) / (n_a * np.pi)) * np.min(l_cells)), 2)
+
+
+class BatchedAssemblySim:
+    def __init__(self, num_envs, n_a, n_g_max, r_avoid, *, device=0, out_dtype=torch.float32, emit_indices=False,
+                 want_prior=True, is_con_self_state=True, is_periodic=False, d_sen=0.4, size_a=0.035, k_ball=30.0,
+                 k_wall=100.0, c_wall=5.0, dt=0.1, vel_max=0.8, mass=1.0, half_width=2.4, half_height=2.4,
+                 exact_occupancy=False):
+        if not torch.cuda.is_available():
+            raise SwarmError("BatchedAssemblySim needs a CUDA device; there is no CPU fallback")
+        if out_dtype not in (torch.float32, torch.float64):
+            raise ValueError("out_dtype must be torch.float32 or torch.float64")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.E, self.n_a, self.n_g_max = int(num_envs), int(n_a), int(n_g_max)
+        self.out_dtype = out_dtype
+        self.emit_indices = bool(emit_indices)
+        self.want_prior = bool(want_prior)
+        self.r_avoid, self.d_sen = float(r_avoid), float(d_sen)
+
+        cfg = SwarmConfig()
+        cfg.struct_size = C.sizeof(SwarmConfig)
+        cfg.device = self.device.index
+        cfg.num_envs, cfg.n_a, cfg.n_g_max = self.E, self.n_a, self.n_g_max
+        cfg.topo_nei_max, cfg.num_obs_grid_max, cfg.num_occupied_grid_max = TOPO_NEI_MAX, NUM_OBS_GRID_MAX, NUM_OCC_GRID_MAX
+        cfg.is_con_self_state, cfg.is_periodic, cfg.want_prior = int(is_con_self_state), int(is_periodic), int(want_prior)
+        cfg.out_dtype = _lib.SWARM_F32 if out_dtype == torch.float32 else _lib.SWARM_F64
+        cfg.emit_indices, cfg.exact_occupancy = int(emit_indices), int(exact_occupancy)
+        cfg.d_sen, cfg.r_avoid, cfg.size_a = d_sen, r_avoid, size_a
+        cfg.k_ball, cfg.k_wall, cfg.c_wall = k_ball, k_wall, c_wall
+        cfg.dt, cfg.vel_max, cfg.mass = dt, vel_max, mass
+        cfg.boundary_pos[:] = [-half_width, half_height, half_width, -half_height]      # assembly.py:193-196
+        self.cfg = cfg
+        self.obs_dim = int(self.lib.swarm_obs_dim(C.byref(cfg)))
+        self.n_g_pad = int(self.lib.swarm_grid_pad(self.n_g_max))
+
+        E, n, dev = self.E, self.n_a, self.device
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)   # noqa: E731
+        self.p = z(E, 2, n, dtype=torch.float64)
+        self.dp = z(E, 2, n, dtype=torch.float64)
+        self._grid = z(E, self.n_g_pad, 2, dtype=torch.float64)
+        self._n_g = z(E, dtype=torch.int32)
+        self._in_thresh = z(E, dtype=torch.float64)
+        self.obs = z(E, self.obs_dim, n, dtype=out_dtype)
+        self.reward = z(E, 1, n, dtype=out_dtype)
+        self.done = z(E, 1, n, dtype=torch.bool)
+        self._a_prior = [z(E, 2, n, dtype=out_dtype), z(E, 2, n, dtype=out_dtype)]
+        self.neighbor_index = torch.full((E, n, TOPO_NEI_MAX), -1, dtype=torch.int32, device=dev)
+        self.in_flags = z(E, n, dtype=torch.int32)
+        if emit_indices:
+            self.nearest_cell = z(E, n, dtype=torch.int32)
+            self.sensed_index = torch.full((E, n, NUM_OBS_GRID_MAX), -1, dtype=torch.int32, device=dev)
+            self.occupied_index = torch.full((E, n, NUM_OCC_GRID_MAX), -1, dtype=torch.int32, device=dev)
+        else:
+            self.nearest_cell = self.sensed_index = self.occupied_index = None
+
+        buf = SwarmBuffers()
+        buf.struct_size = C.sizeof(SwarmBuffers)
+        buf.p, buf.dp, buf.grid = self.p.data_ptr(), self.dp.data_ptr(), self._grid.data_ptr()
+        buf.n_g, buf.in_thresh = self._n_g.data_ptr(), self._in_thresh.data_ptr()
+        buf.obs, buf.reward = self.obs.data_ptr(), self.reward.data_ptr()
+        buf.a_prior[0], buf.a_prior[1] = self._a_prior[0].data_ptr(), self._a_prior[1].data_ptr()
+        buf.neighbor_index, buf.in_flags = self.neighbor_index.data_ptr(), self.in_flags.data_ptr()
+        if emit_indices:
+            buf.nearest_cell = self.nearest_cell.data_ptr()
+            buf.sensed_index, buf.occupied_index = self.sensed_index.data_ptr(), self.occupied_index.data_ptr()
+        self._buf = buf
+        h = C.c_void_p()
+        check(self.lib.swarm_create(C.byref(cfg), C.byref(buf), C.byref(h)), "swarm_create")
+        self._h = h
+        self.l_cell = np.zeros(E)
+        self.n_g = np.zeros(E, dtype=np.int32)
+
+    # ------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.swarm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------------------------------------
+    def set_grid(self, grid, n_g, l_cell, env0=0):
+        """grid: [count, 2, n_g_max] float64 (numpy or CUDA tensor), each env's [2, n_g] grid_center stored
+        contiguously at the start of its block (i.e. `block.reshape(-1)[:2*n_g].reshape(2, n_g)`);
+        n_g, l_cell: [count] host arrays (assembly.py:163,179,187)."""
+        n_g = np.ascontiguousarray(n_g, dtype=np.int32).reshape(-1)
+        l_cell = np.ascontiguousarray(l_cell, dtype=np.float64).reshape(-1)
+        count = n_g.shape[0]
+        on_dev = isinstance(grid, torch.Tensor) and grid.is_cuda
+        if on_dev:
+            g = grid.to(torch.float64).contiguous()
+            assert g.numel() == count * 2 * self.n_g_max
+            ptr = g.data_ptr()
+        else:
+            g = np.ascontiguousarray(grid, dtype=np.float64)
+            assert g.size == count * 2 * self.n_g_max, (g.shape, count, self.n_g_max)
+            ptr = g.ctypes.data
+        check(self.lib.swarm_set_grid(self._h, env0, count, C.c_void_p(ptr), int(on_dev), C.c_void_p(n_g.ctypes.data),
+                                      C.c_void_p(l_cell.ctypes.data), self._stream()), "swarm_set_grid")
+        self.n_g[env0:env0 + count] = n_g
+        self.l_cell[env0:env0 + count] = l_cell
+
+    @staticmethod
+    def pack_grids(grids, n_g_max):
+        """list of [2, n_g] arrays -> ([count, 2*n_g_max] block array, n_g[count])"""
+        out = np.zeros((len(grids), 2 * n_g_max))
+        n_g = np.zeros(len(grids), dtype=np.int32)
+        for k, g in enumerate(grids):
+            g = np.ascontiguousarray(g, dtype=np.float64)
+            out[k, :g.size] = g.reshape(-1)
+            n_g[k] = g.shape[1]
+        return out, n_g
+
+    def set_state(self, p, dp):
+        """Overwrite positions / velocities ([E,2,n_a]); like assigning env.p / env.dp in the reference."""
+        self.p.copy_(torch.as_tensor(p, dtype=torch.float64).reshape(self.E, 2, self.n_a))
+        self.dp.copy_(torch.as_tensor(dp, dtype=torch.float64).reshape(self.E, 2, self.n_a))
+        check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
+
+    def mark_state_dirty(self):
+        check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
+
+    # ------------------------------------------------------------------------------------------------
+    def observe(self):
+        """Tail of reset() (assembly.py:221): observation of the current state."""
+        check(self.lib.swarm_observe(self._h, self._stream()), "swarm_observe")
+        return self.obs
+
+    def step(self, act):
+        """act: CUDA tensor [E, 2, n_a], float32 or float64.  Returns the reference's 5-tuple (assembly.py:666)
+        as device tensors; `info` is None."""
+        if not (isinstance(act, torch.Tensor) and act.is_cuda):
+            raise TypeError("step() takes a CUDA tensor; use step_host() for host buffers")
+        if act.dtype not in (torch.float32, torch.float64):
+            act = act.to(torch.float32)
+        act = act.contiguous()
+        assert act.numel() == self.E * 2 * self.n_a
+        dt = _lib.SWARM_F32 if act.dtype == torch.float32 else _lib.SWARM_F64
+        check(self.lib.swarm_step(self._h, C.c_void_p(act.data_ptr()), dt, self._stream()), "swarm_step")
+        return self.obs, self.reward, self.done, None, (self.a_prior if self.want_prior else None)
+
+    def step_host(self, act_host, obs_host=None, reward_host=None, a_prior_host=None):
+        """Same step through host buffers (numpy / pinned torch CPU tensors): H2D actions, step, D2H results."""
+        def ptr(a):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                assert not a.is_cuda and a.is_contiguous()
+                return C.c_void_p(a.data_ptr())
+            assert a.flags["C_CONTIGUOUS"]
+            return C.c_void_p(a.ctypes.data)
+        if isinstance(act_host, np.ndarray):
+            assert act_host.dtype == np.float32
+        else:
+            assert act_host.dtype == torch.float32
+        check(self.lib.swarm_step_host(self._h, ptr(act_host), ptr(obs_host), ptr(reward_host), ptr(a_prior_host),
+                                       self._stream()), "swarm_step_host")
+
+    @property
+    def a_prior(self):
+        """a_prior returned by the most recent step (double-buffered on the device)."""
+        ptr = self.lib.swarm_a_prior_ptr(self._h)
+        return self._a_prior[0] if ptr == self._a_prior[0].data_ptr() else self._a_prior[1]
+
+    def fill_actions(self, out, seed, step, env_offset=0):
+        """Synthetic U(-1,1) float32 actions [E,2,n_a], identical to oracle.fill_actions for the same keys."""
+        assert out.is_cuda and out.dtype == torch.float32 and out.numel() == self.E * 2 * self.n_a
+        check(self.lib.swarm_fill_actions(self._h, seed, step, env_offset, C.c_void_p(out.data_ptr()), self._stream()),
+              "swarm_fill_actions")
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.lib.swarm_launch_count(self._h))
+
+    def kernel_geometry(self):
+        t, s, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.lib.swarm_kernel_geometry(self._h, C.byref(t), C.byref(s), C.byref(c)), "swarm_kernel_geometry")
+        return dict(threads_per_cta=t.value, smem_bytes=s.value, ctas=c.value)
+
+    # ------------------------------------------------------------------------------------------------
+    def algorithmic_bytes_per_agent_step(self, mean_n_g=None):
+        """Unavoidable HBM traffic of one step per agent, for the roofline figure."""
+        osz = 4 if self.out_dtype == torch.float32 else 8
+        ng = float(np.mean(self.n_g)) if mean_n_g is None else mean_n_g
+        b = 2 * 4                      # read action (f32 x 2)
+        b += 4 * 8 + 4 * 8             # read + write p, dp
+        b += self.obs_dim * osz        # write obs
+        b += osz                       # write reward
+        b += (2 * osz if self.want_prior else 0)       # write next prior
+        b += TOPO_NEI_MAX * 4 + 4      # write neighbor_index + in_flags
+        b += 2 * 8 * math.ceil(ng / 32) * 32 / self.n_a   # read the env's cell list once per env
+        if self.emit_indices:
+            b += (NUM_OBS_GRID_MAX + NUM_OCC_GRID_MAX + 1) * 4
+        return b

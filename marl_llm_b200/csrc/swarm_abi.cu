@@ -1,0 +1,506 @@
+// swarm_abi.cu — host side of the C ABI declared in include/swarm_b200.h.
+//
+// There is no CPU implementation behind these entry points: without a usable sm_100 device the batched calls
+// return SWARM_ERR_NO_DEVICE / SWARM_ERR_CUDA and the legacy (void) calls print the CUDA error and abort.
+#include "swarm_kernels.cuh"
+#include "../../include/swarm_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace swarm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) { g_last_error = msg; return code; }
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t err__ = (expr);                                                                    \
+        if (err__ != cudaSuccess)                                                                      \
+            return fail(SWARM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));        \
+    } while (0)
+
+// smallest double T with sqrt_rn(T) >= d, i.e.  sqrt_rn(s) < d  <=>  s < T   (sqrt_rn is monotone)
+double thresh_lt(double d) {
+    if (!(d > 0)) return 0.0;
+    double t = d * d;
+    while (std::sqrt(t) >= d) t = std::nextafter(t, -INFINITY);
+    while (std::sqrt(std::nextafter(t, INFINITY)) < d) t = std::nextafter(t, INFINITY);
+    return std::nextafter(t, INFINITY);
+}
+// largest double U with sqrt_rn(U) <= h, i.e.  sqrt_rn(s) <= h  <=>  s <= U
+double thresh_le(double h) {
+    if (h < 0) return -1.0;
+    double t = h * h;
+    while (std::sqrt(t) > h) t = std::nextafter(t, -INFINITY);
+    while (std::sqrt(std::nextafter(t, INFINITY)) <= h) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
+int round32(int n) { return (n + 31) & ~31; }
+
+size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit) {
+    size_t b = (size_t)n_g_pad * sizeof(double2) + (size_t)4 * nt * sizeof(double);
+    b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
+    b += (size_t)((n_words + 1) & ~1) * 4 + 8;
+    return b;
+}
+
+typedef void (*step_fn_t)(const KParams);
+
+template <typename OUT, int MAXT>
+step_fn_t pick2(bool dyn, bool emit) {
+    if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, MAXT> : (step_fn_t)k_step<OUT, true, false, MAXT>;
+    return emit ? (step_fn_t)k_step<OUT, false, true, MAXT> : (step_fn_t)k_step<OUT, false, false, MAXT>;
+}
+step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt) {
+    if (nt <= 128) return f32 ? pick2<float, 128>(dyn, emit) : pick2<double, 128>(dyn, emit);
+    return f32 ? pick2<float, 1024>(dyn, emit) : pick2<double, 1024>(dyn, emit);
+}
+
+void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool self_state, bool want_prior,
+                    bool exact_occ, double d_sen, double r_avoid, double size_a, double k_ball, double k_wall,
+                    double c_wall, double dt, double vel_max, double mass, const double *bp) {
+    K.n_a = n_a;
+    K.n_g_pad = round32(n_g_max);
+    K.n_words = K.n_g_pad / 32;
+    K.n_obs_max = n_obs;
+    K.n_occ_max = n_occ;
+    K.self_state = self_state;
+    K.obs_dim = 2 * 2 * (TOPO + 1 + (self_state ? 1 : 0)) + 2 * n_obs;    // ENV:801
+    K.want_prior = want_prior;
+    K.exact_occ = exact_occ;
+    K.d_sen = d_sen; K.r_avoid = r_avoid; K.size_a = size_a; K.two_size = size_a + size_a;   // ENV:785-786
+    K.k_ball = k_ball; K.k_wall = k_wall; K.c_wall = c_wall; K.dt = dt; K.vel_max = vel_max; K.mass = mass;
+    K.bx_min = bp[0]; K.by_max = bp[1]; K.bx_max = bp[2]; K.by_min = bp[3];
+    K.T_sen = thresh_lt(d_sen);
+    K.T_col = thresh_lt(K.two_size);
+    const double d_near = d_sen + r_avoid / 2.0;                          // CPP:161
+    K.T_near = thresh_lt(d_near);
+    K.T_near_hi = (d_near * (1.0 + 1e-9)) * (d_near * (1.0 + 1e-9));
+    K.U_occ = thresh_le(r_avoid / 2.0);                                   // CPP:185
+}
+
+double in_shape_thresh(double l_cell) { return thresh_lt(std::sqrt(2.0) * l_cell / 2); }   // CPP:889
+
+}  // namespace
+
+struct swarm_sim {
+    swarm_config cfg;
+    swarm_buffers buf;
+    KParams K;
+    int nt;                 // threads per CTA
+    size_t smem;
+    int pending;            // a_prior buffer holding the prior of the CURRENT state
+    int last;               // a_prior buffer returned by the most recent step
+    bool prior_dirty;       // state / grid changed behind the kernel's back
+    bool observed;          // at least one observe/step ran (neighbor_index is meaningful)
+    int64_t launches;
+    double *d_stage; size_t stage_cap;     // set_grid staging (reference-layout grid)
+    float *d_act; size_t act_cap;          // step_host action staging
+};
+
+extern "C" {
+
+int swarm_abi_version(void) { return 1; }
+/* host-only helper exposed for tests: the squared-distance threshold equivalent to sqrt(s) < d (le=0) or <= d (le=1) */
+double swarm_sqrt_threshold(double d, int le) { return le ? thresh_le(d) : thresh_lt(d); }
+const char *swarm_last_error(void) { return g_last_error.c_str(); }
+int32_t swarm_grid_pad(int32_t n_g_max) { return round32(n_g_max); }
+int32_t swarm_obs_dim(const swarm_config *cfg) {
+    return 2 * 2 * (TOPO + 1 + (cfg->is_con_self_state ? 1 : 0)) + 2 * cfg->num_obs_grid_max;
+}
+
+int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **out) {
+    if (!cfg || !buf || !out) return fail(SWARM_ERR_INVALID, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(swarm_config) || buf->struct_size != (int32_t)sizeof(swarm_buffers))
+        return fail(SWARM_ERR_INVALID, "struct_size mismatch (ABI)");
+    if (cfg->num_envs <= 0 || cfg->n_a <= 0 || cfg->n_g_max <= 0) return fail(SWARM_ERR_INVALID, "sizes must be positive");
+    if (cfg->topo_nei_max != TOPO) return fail(SWARM_ERR_UNSUPPORTED, "topo_nei_max must be 6");
+    if (cfg->n_a > 1024) return fail(SWARM_ERR_UNSUPPORTED, "n_a > 1024 not supported by the fused kernel");
+    if (cfg->is_periodic) return fail(SWARM_ERR_UNSUPPORTED, "periodic boundaries (is_boundary=False) not implemented");
+    if (cfg->num_obs_grid_max < 2 || cfg->num_occupied_grid_max < 2) return fail(SWARM_ERR_INVALID, "list caps must be >= 2");
+    if (cfg->out_dtype != SWARM_F64 && cfg->out_dtype != SWARM_F32) return fail(SWARM_ERR_INVALID, "bad out_dtype");
+    if (!buf->p || !buf->dp || !buf->grid || !buf->n_g || !buf->in_thresh || !buf->obs || !buf->reward ||
+        !buf->a_prior[0] || !buf->a_prior[1] || !buf->neighbor_index || !buf->in_flags)
+        return fail(SWARM_ERR_INVALID, "required device buffer is NULL");
+    if (cfg->emit_indices && (!buf->sensed_index || !buf->occupied_index || !buf->nearest_cell))
+        return fail(SWARM_ERR_INVALID, "emit_indices needs sensed_index / occupied_index / nearest_cell buffers");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SWARM_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SWARM_ERR_INVALID, "device ordinal out of range");
+    CU_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(SWARM_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+
+    swarm_sim *s = new swarm_sim();
+    s->cfg = *cfg; s->buf = *buf;
+    memset(&s->K, 0, sizeof(KParams));
+    fill_constants(s->K, cfg->n_a, cfg->n_g_max, cfg->num_obs_grid_max, cfg->num_occupied_grid_max,
+                   cfg->is_con_self_state != 0, cfg->want_prior != 0, cfg->exact_occupancy != 0, cfg->d_sen,
+                   cfg->r_avoid, cfg->size_a, cfg->k_ball, cfg->k_wall, cfg->c_wall, cfg->dt, cfg->vel_max,
+                   cfg->mass, cfg->boundary_pos);
+    KParams &K = s->K;
+    K.E = cfg->num_envs;
+    K.p = buf->p; K.dp = buf->dp; K.grid = reinterpret_cast<const double2 *>(buf->grid);
+    K.n_g = buf->n_g; K.in_thresh = buf->in_thresh;
+    K.obs = buf->obs; K.reward = buf->reward;
+    K.nbr = buf->neighbor_index; K.in_flags = buf->in_flags; K.nearest = buf->nearest_cell;
+    K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
+    s->nt = round32(cfg->n_a);
+    s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0);
+    if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete s;
+        return fail(SWARM_ERR_UNSUPPORTED, "n_a x n_g_max needs more shared memory than one SM has");
+    }
+    for (int dyn = 0; dyn < 2; ++dyn) {
+        step_fn_t f = pick_step(cfg->out_dtype == SWARM_F32, dyn != 0, cfg->emit_indices != 0, s->nt);
+        cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+        if (e != cudaSuccess) { delete s; return fail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    }
+    s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
+    s->d_stage = nullptr; s->stage_cap = 0; s->d_act = nullptr; s->act_cap = 0;
+    *out = s;
+    return SWARM_OK;
+}
+
+int swarm_destroy(swarm_sim *s) {
+    if (!s) return SWARM_OK;
+    cudaSetDevice(s->cfg.device);
+    if (s->d_stage) cudaFree(s->d_stage);
+    if (s->d_act) cudaFree(s->d_act);
+    delete s;
+    return SWARM_OK;
+}
+
+int swarm_set_grid(swarm_sim *s, int32_t env0, int32_t count, const double *grid, int grid_on_device,
+                   const int32_t *n_g, const double *l_cell, void *stream) {
+    if (!s || !grid || !n_g || !l_cell) return fail(SWARM_ERR_INVALID, "null argument");
+    if (env0 < 0 || count <= 0 || env0 + count > s->cfg.num_envs) return fail(SWARM_ERR_INVALID, "env range out of bounds");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const int ngm = s->cfg.n_g_max;
+    std::vector<double> thr(count);
+    for (int k = 0; k < count; ++k) {
+        if (n_g[k] <= 0 || n_g[k] > ngm) return fail(SWARM_ERR_INVALID, "n_g out of range (0, n_g_max]");
+        thr[k] = in_shape_thresh(l_cell[k]);
+    }
+    CU_TRY(cudaMemcpyAsync(s->buf.n_g + env0, n_g, sizeof(int32_t) * count, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(s->buf.in_thresh + env0, thr.data(), sizeof(double) * count, cudaMemcpyHostToDevice, st));
+    const double *src = grid;
+    if (!grid_on_device) {
+        const size_t need = (size_t)count * 2 * ngm;
+        if (need > s->stage_cap) {
+            if (s->d_stage) CU_TRY(cudaFree(s->d_stage));
+            s->d_stage = nullptr; s->stage_cap = 0;
+            CU_TRY(cudaMalloc(&s->d_stage, need * sizeof(double)));
+            s->stage_cap = need;
+        }
+        CU_TRY(cudaMemcpyAsync(s->d_stage, grid, need * sizeof(double), cudaMemcpyHostToDevice, st));
+        src = s->d_stage;
+    }
+    k_pack_grid<<<count, 128, 0, st>>>(src, (long)2 * ngm, s->buf.n_g + env0, s->K.n_g_pad,
+                                       reinterpret_cast<double2 *>(s->buf.grid) + (size_t)env0 * s->K.n_g_pad);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    // thr/n_g host vectors must outlive the async copies
+    CU_TRY(cudaStreamSynchronize(st));
+    s->prior_dirty = true;
+    return SWARM_OK;
+}
+
+int swarm_mark_state_dirty(swarm_sim *s) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    s->prior_dirty = true;
+    return SWARM_OK;
+}
+
+static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, cudaStream_t st) {
+    KParams K = s->K;
+    K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
+    K.prior_next = s->buf.a_prior[dyn ? (1 - s->pending) : s->pending];
+    step_fn_t f = pick_step(s->cfg.out_dtype == SWARM_F32, dyn, s->cfg.emit_indices != 0, s->nt);
+    f<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    return SWARM_OK;
+}
+
+int swarm_observe(swarm_sim *s, void *stream) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    int rc = launch_step(s, false, nullptr, SWARM_F32, (cudaStream_t)stream);
+    if (rc != SWARM_OK) return rc;
+    s->prior_dirty = false; s->observed = true;
+    return SWARM_OK;
+}
+
+int swarm_step(swarm_sim *s, const void *act, int act_dtype, void *stream) {
+    if (!s || !act) return fail(SWARM_ERR_INVALID, "null argument");
+    if (act_dtype != SWARM_F32 && act_dtype != SWARM_F64) return fail(SWARM_ERR_INVALID, "bad act_dtype");
+    if (!s->observed) return fail(SWARM_ERR_INVALID, "swarm_step before swarm_observe (reset)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    if (s->cfg.want_prior && s->prior_dirty) {
+        // ENV:613-624 semantics: prior from the current p/dp/grid and the neighbour list of the last observation
+        const int n_a = s->cfg.n_a;
+        const int th = n_a < 256 ? round32(n_a) : 256;
+        if (s->cfg.out_dtype == SWARM_F32)
+            k_prior<float><<<s->cfg.num_envs, th, 0, st>>>(n_a, TOPO, s->K.p, s->K.dp, s->K.grid, s->K.n_g_pad, s->K.n_g,
+                                                         s->K.in_thresh, s->K.nbr, s->K.r_avoid, (float *)s->buf.a_prior[s->pending]);
+        else
+            k_prior<double><<<s->cfg.num_envs, th, 0, st>>>(n_a, TOPO, s->K.p, s->K.dp, s->K.grid, s->K.n_g_pad, s->K.n_g,
+                                                          s->K.in_thresh, s->K.nbr, s->K.r_avoid, (double *)s->buf.a_prior[s->pending]);
+        CU_TRY(cudaGetLastError());
+        s->launches++;
+    }
+    int rc = launch_step(s, true, act, act_dtype, st);
+    if (rc != SWARM_OK) return rc;
+    s->last = s->pending;
+    s->pending = 1 - s->pending;
+    s->prior_dirty = false;
+    return SWARM_OK;
+}
+
+void *swarm_a_prior_ptr(swarm_sim *s) { return s ? s->buf.a_prior[s->last] : nullptr; }
+
+int swarm_step_host(swarm_sim *s, const float *act_host, void *obs_host, void *reward_host, void *a_prior_host, void *stream) {
+    if (!s || !act_host) return fail(SWARM_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const size_t E = s->cfg.num_envs, n = s->cfg.n_a;
+    const size_t nact = E * 2 * n;
+    if (nact > s->act_cap) {
+        if (s->d_act) CU_TRY(cudaFree(s->d_act));
+        s->d_act = nullptr; s->act_cap = 0;
+        CU_TRY(cudaMalloc(&s->d_act, nact * sizeof(float)));
+        s->act_cap = nact;
+    }
+    CU_TRY(cudaMemcpyAsync(s->d_act, act_host, nact * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = swarm_step(s, s->d_act, SWARM_F32, stream);
+    if (rc != SWARM_OK) return rc;
+    const size_t osz = s->cfg.out_dtype == SWARM_F32 ? 4 : 8;
+    if (obs_host) CU_TRY(cudaMemcpyAsync(obs_host, s->buf.obs, E * s->K.obs_dim * n * osz, cudaMemcpyDeviceToHost, st));
+    if (reward_host) CU_TRY(cudaMemcpyAsync(reward_host, s->buf.reward, E * n * osz, cudaMemcpyDeviceToHost, st));
+    if (a_prior_host) CU_TRY(cudaMemcpyAsync(a_prior_host, s->buf.a_prior[s->last], E * 2 * n * osz, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return SWARM_OK;
+}
+
+int swarm_fill_actions(swarm_sim *s, uint64_t seed, uint64_t step, uint64_t env_offset, float *act_dev, void *stream) {
+    if (!s || !act_dev) return fail(SWARM_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const long per_env = 2L * s->cfg.n_a, total = per_env * s->cfg.num_envs;
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 16);
+    k_fill_actions<<<blocks, 256, 0, (cudaStream_t)stream>>>(total, (int)per_env, seed, step, env_offset, act_dev);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    return SWARM_OK;
+}
+
+int64_t swarm_launch_count(const swarm_sim *s) { return s ? s->launches : 0; }
+
+int swarm_kernel_geometry(const swarm_sim *s, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *ctas) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    if (threads_per_cta) *threads_per_cta = s->nt;
+    if (smem_bytes) *smem_bytes = (int32_t)s->smem;
+    if (ctas) *ctas = s->cfg.num_envs;
+    return SWARM_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================
+// Legacy stateless entry points (HOST pointers).  Scratch device memory comes from a process-wide arena.
+// =====================================================================================================
+namespace {
+
+std::mutex g_legacy_mutex;
+unsigned char *g_arena = nullptr;
+size_t g_arena_cap = 0;
+
+[[noreturn]] void legacy_die(const char *where, const std::string &msg) {
+    fprintf(stderr, "[swarm_b200] %s: %s (no CPU fallback exists; aborting)\n", where, msg.c_str());
+    abort();
+}
+#define LEG_TRY(where, expr)                                                             \
+    do {                                                                                 \
+        cudaError_t err__ = (expr);                                                      \
+        if (err__ != cudaSuccess) legacy_die(where, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+struct Arena {
+    size_t off = 0;
+    explicit Arena(size_t need, const char *where) {
+        need += 4096;
+        if (need > g_arena_cap) {
+            if (g_arena) LEG_TRY(where, cudaFree(g_arena));
+            g_arena = nullptr; g_arena_cap = 0;
+            LEG_TRY(where, cudaMalloc(&g_arena, need));
+            g_arena_cap = need;
+        }
+    }
+    template <typename T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *ptr = reinterpret_cast<T *>(g_arena + off);
+        off += count * sizeof(T);
+        return ptr;
+    }
+};
+
+size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+void _get_observation(double *p, double *dp, double *heading, double *obs, double *boundary_pos, double *grid_center,
+                      int *neighbor_index, int *in_flags, int *sensed_index, int *occupied_index, double d_sen,
+                      double r_avoid, double l_cell, double Vel_max, int topo_nei_max, int num_obs_grid_max,
+                      int num_occupied_grid_max, int n_a, int n_g, int obs_dim_agent, int dim, bool *condition) {
+    const char *W = "_get_observation";
+    (void)heading; (void)Vel_max;
+    if (dim != 2 || topo_nei_max != TOPO) legacy_die(W, "only dim == 2 and topo_nei_max == 6 are supported");
+    if (condition[0]) legacy_die(W, "periodic boundaries are not implemented");
+    if (!condition[1]) legacy_die(W, "only Cartesian dynamics are implemented");
+    if (n_a > 1024 || n_a <= 0 || n_g <= 0) legacy_die(W, "n_a must be in [1,1024] and n_g positive");
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    KParams K; memset(&K, 0, sizeof(K));
+    fill_constants(K, n_a, n_g, num_obs_grid_max, num_occupied_grid_max, condition[2], false, false, d_sen, r_avoid,
+                   0.035, 30.0, 100.0, 5.0, 0.1, 0.8, 1.0, boundary_pos);
+    if (K.obs_dim != obs_dim_agent) legacy_die(W, "obs_dim_agent does not match 2*2*(6+1+self)+2*num_obs_grid_max");
+    K.E = 1;
+    const int nt = round32(n_a);
+    const size_t smem = step_smem_bytes(nt, K.n_g_pad, K.n_words, true);
+    const size_t n_obs = (size_t)K.obs_dim * n_a;
+    Arena A(al(16 * n_a * 8) + al(2 * n_g * 8) + al(K.n_g_pad * 16) + al(n_obs * 8) + al(n_a * 8 * 3) + al(n_a * TOPO * 4) +
+            al(n_a * 8) + al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * num_occupied_grid_max * 4) + 16 * 256, W);
+    double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_gsrc = A.take<double>(2 * n_g);
+    double2 *d_grid = A.take<double2>(K.n_g_pad);
+    int *d_ng = A.take<int>(1); double *d_thr = A.take<double>(1);
+    double *d_obs = A.take<double>(n_obs), *d_rew = A.take<double>(n_a), *d_prior = A.take<double>(2 * n_a);
+    int *d_nbr = A.take<int>(n_a * TOPO), *d_inf = A.take<int>(n_a), *d_near = A.take<int>(n_a);
+    int *d_sidx = A.take<int>((size_t)n_a * num_obs_grid_max), *d_occ = A.take<int>((size_t)n_a * num_occupied_grid_max);
+    const double thr = in_shape_thresh(l_cell);
+    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_dp, dp, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid);
+    K.p = d_p; K.dp = d_dp; K.grid = d_grid; K.n_g = d_ng; K.in_thresh = d_thr;
+    K.obs = d_obs; K.reward = d_rew; K.prior_next = d_prior;
+    K.nbr = d_nbr; K.in_flags = d_inf; K.nearest = d_near; K.sensed = d_sidx; K.occupied = d_occ;
+    step_fn_t f = pick_step(false, false, true, nt);
+    LEG_TRY(W, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    f<<<1, nt, smem>>>(K);
+    LEG_TRY(W, cudaGetLastError());
+    LEG_TRY(W, cudaMemcpy(obs, d_obs, n_obs * 8, cudaMemcpyDeviceToHost));
+    LEG_TRY(W, cudaMemcpy(neighbor_index, d_nbr, (size_t)n_a * TOPO * 4, cudaMemcpyDeviceToHost));
+    LEG_TRY(W, cudaMemcpy(in_flags, d_inf, (size_t)n_a * 4, cudaMemcpyDeviceToHost));
+    LEG_TRY(W, cudaMemcpy(sensed_index, d_sidx, (size_t)n_a * num_obs_grid_max * 4, cudaMemcpyDeviceToHost));
+    LEG_TRY(W, cudaMemcpy(occupied_index, d_occ, (size_t)n_a * num_occupied_grid_max * 4, cudaMemcpyDeviceToHost));
+}
+
+void _get_reward(double *p, double *dp, double *heading, double *act, double *reward, double *boundary_pos,
+                 double *grid_center, int *neighbor_index, int *in_flags, int *sensed_index, int *occupied_index,
+                 double d_sen, double r_avoid, double l_cell, int topo_nei_max, int num_obs_grid_max,
+                 int num_occupied_grid_max, int n_a, int n_g, int dim, bool *condition, bool *is_collide_b2b,
+                 bool *is_collide_b2w, double *coefficients) {
+    const char *W = "_get_reward";
+    (void)dp; (void)heading; (void)act; (void)boundary_pos; (void)occupied_index; (void)l_cell;
+    (void)num_occupied_grid_max; (void)is_collide_b2b; (void)is_collide_b2w; (void)coefficients;
+    if (dim != 2) legacy_die(W, "only dim == 2 is supported");
+    if (condition[0]) legacy_die(W, "periodic boundaries are not implemented");
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    Arena A(al(2 * n_a * 8) + al(2 * (size_t)n_g * 8) + al((size_t)n_a * topo_nei_max * 4) + al(n_a * 4) +
+            al((size_t)n_a * num_obs_grid_max * 4) + al(n_a * 8) + 8 * 256, W);
+    double *d_p = A.take<double>(2 * n_a), *d_g = A.take<double>(2 * (size_t)n_g), *d_r = A.take<double>(n_a);
+    int *d_nbr = A.take<int>((size_t)n_a * topo_nei_max), *d_inf = A.take<int>(n_a);
+    int *d_sidx = A.take<int>((size_t)n_a * num_obs_grid_max);
+    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_g, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_inf, in_flags, (size_t)n_a * 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_sidx, sensed_index, (size_t)n_a * num_obs_grid_max * 4, cudaMemcpyHostToDevice));
+    k_legacy_reward<<<(n_a + 127) / 128, 128>>>(d_p, d_g, d_nbr, d_inf, d_sidx, n_a, n_g, topo_nei_max, num_obs_grid_max,
+                                               d_sen, r_avoid, condition[3], condition[4], d_r);
+    LEG_TRY(W, cudaGetLastError());
+    LEG_TRY(W, cudaMemcpy(reward, d_r, (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+}
+
+void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide_b2b, double *boundary_pos,
+                 double *d_b2b_center, int n_a, int dim, double k_ball, bool is_periodic) {
+    const char *W = "_sf_b2b_all";
+    (void)boundary_pos;
+    if (dim != 2) legacy_die(W, "only dim == 2 is supported");
+    if (is_periodic) legacy_die(W, "periodic boundaries are not implemented");
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    const size_t nn = (size_t)n_a * n_a;
+    Arena A(al(2 * n_a * 8) * 2 + al(nn * 8) * 2 + al(nn) + 8 * 256, W);
+    double *d_p = A.take<double>(2 * n_a), *d_sf = A.take<double>(2 * n_a);
+    double *d_e = A.take<double>(nn), *d_c = A.take<double>(nn);
+    unsigned char *d_col = A.take<unsigned char>(nn);
+    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_e, d_b2b_edge, nn * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_c, d_b2b_center, nn * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_col, is_collide_b2b, nn, cudaMemcpyHostToDevice));
+    k_legacy_sf_b2b<<<(n_a + 127) / 128, 128>>>(d_p, d_e, d_col, d_c, n_a, k_ball, d_sf);
+    LEG_TRY(W, cudaGetLastError());
+    LEG_TRY(W, cudaMemcpy(sf_b2b, d_sf, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+}
+
+void _get_dist_b2w(double *p, double *r, double *d_b2w, bool *isCollision, int dim, int n_a, double *boundary_pos) {
+    const char *W = "_get_dist_b2w";
+    if (dim != 2) legacy_die(W, "only dim == 2 is supported");
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    Arena A(al(2 * n_a * 8) + al(n_a * 8) + al(4 * n_a * 8) + al(4 * n_a) + al(32) + 8 * 256, W);
+    double *d_p = A.take<double>(2 * n_a), *d_r = A.take<double>(n_a), *d_d = A.take<double>(4 * n_a), *d_bp = A.take<double>(4);
+    unsigned char *d_col = A.take<unsigned char>(4 * n_a);
+    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_r, r, (size_t)n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_bp, boundary_pos, 32, cudaMemcpyHostToDevice));
+    k_legacy_b2w<<<(n_a + 127) / 128, 128>>>(d_p, d_r, d_bp, n_a, d_d, d_col);
+    LEG_TRY(W, cudaGetLastError());
+    LEG_TRY(W, cudaMemcpy(d_b2w, d_d, 4 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+    LEG_TRY(W, cudaMemcpy(isCollision, d_col, 4 * (size_t)n_a, cudaMemcpyDeviceToHost));
+}
+
+void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_center, int *neighbor_index, double d_sen,
+                          double r_avoid, double l_cell, int topo_nei_max, int n_a, int n_g, int dim) {
+    const char *W = "calculateActionPrior";
+    (void)d_sen;
+    if (dim != 2) legacy_die(W, "only dim == 2 is supported");
+    std::lock_guard<std::mutex> lock(g_legacy_mutex);
+    const int n_g_pad = round32(n_g);
+    Arena A(al(2 * n_a * 8) * 3 + al(2 * (size_t)n_g * 8) + al((size_t)n_g_pad * 16) + al((size_t)n_a * topo_nei_max * 4) + 10 * 256, W);
+    double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_out = A.take<double>(2 * n_a);
+    double *d_gsrc = A.take<double>(2 * (size_t)n_g);
+    double2 *d_grid = A.take<double2>(n_g_pad);
+    int *d_nbr = A.take<int>((size_t)n_a * topo_nei_max), *d_ng = A.take<int>(1);
+    double *d_thr = A.take<double>(1);
+    const double thr = in_shape_thresh(l_cell);
+    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_dp, dp, 2 * n_a * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid);
+    k_prior<double><<<1, n_a < 256 ? round32(n_a) : 256>>>(n_a, topo_nei_max, d_p, d_dp, d_grid, n_g_pad, d_ng, d_thr, d_nbr, r_avoid, d_out);
+    LEG_TRY(W, cudaGetLastError());
+    LEG_TRY(W, cudaMemcpy(a_prior, d_out, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+}
+
+}  // extern "C"

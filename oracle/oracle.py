@@ -84,12 +84,12 @@ class OracleBatch:
     reference; arrays are [E, ...] stacks of them.  Grid blocks are [E, 2, ng_max] (row-major,
     each env's [2, n_g] matrix stored contiguously at the start of its block)."""
 
-    def __init__(self, params_list, nthreads=1):
+    def __init__(self, params_list, nthreads=1, ng_max=None):
         self.E = len(params_list)
         self.params = (OrcParams * self.E)(*params_list)
         P0 = params_list[0]
         self.n_a, self.obs_dim = P0.n_a, P0.obs_dim
-        self.ng_max = max(p.n_g for p in params_list)
+        self.ng_max = max(max(p.n_g for p in params_list), ng_max or 0)
         E, n = self.E, self.n_a
         self.p = np.zeros((E, 2, n))
         self.dp = np.zeros((E, 2, n))

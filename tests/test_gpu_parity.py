@@ -1,0 +1,319 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the golden trajectories recorded from the
+unmodified reference and (b) the C oracle on seeded inputs.  Integer/index outputs, done flags and — because the
+kernels reproduce the reference's fp64 operation order without FMA — positions, velocities, observations, rewards
+and priors are all required to be BIT-EXACT (the north star only asks for 1e-5 relative on the floating-point ones)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests.helpers import GOLDEN_CASES, goal_seeking_action, load_golden, load_shapes, replay_golden, reset_like_reference
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sim(E, n_a, n_g_max, r_avoid, **kw):
+    from marl_llm_b200.batched import BatchedAssemblySim
+    return BatchedAssemblySim(E, n_a, n_g_max, r_avoid, **kw)
+
+
+def sim_snapshot(sim, e=None):
+    sl = slice(None) if e is None else e
+    f = lambda t: None if t is None else t[sl].cpu().numpy()   # noqa: E731
+    return dict(p=f(sim.p), dp=f(sim.dp), obs=f(sim.obs), reward=f(sim.reward), a_prior=f(sim.a_prior),
+                nbr=f(sim.neighbor_index), in_flags=f(sim.in_flags), sensed=f(sim.sensed_index), occupied=f(sim.occupied_index))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_golden_trajectories_bit_exact(case):
+    g = load_golden(case)
+    n_a, n_g = int(g["n_a"]), int(g["n_g"])
+    sim = make_sim(1, n_a, n_g, float(g["r_avoid"]), out_dtype=torch.float64, emit_indices=True, d_sen=float(g["d_sen"]))
+
+    def reset_fn(g):
+        blocks, ng = sim.pack_grids([g["grid_center"]], n_g)
+        sim.set_grid(blocks, ng, [float(g["l_cell"])])
+        sim.set_state(g["p0"][None], g["dp0"][None])
+        sim.observe()
+        return sim_snapshot(sim, 0)
+
+    def step_fn(a):
+        sim.step(torch.from_numpy(a[None]).cuda())
+        return sim_snapshot(sim, 0)
+
+    replay_golden(g, reset_fn, step_fn)
+    assert not sim.done.any()
+
+
+def build_batch(E, n_a, seed, shapes=None, shape_of=None):
+    shapes = shapes or load_shapes()
+    rng = np.random.RandomState(seed)
+    r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    params, grids, P, DP = [], [], [], []
+    for e in range(E):
+        k, grid, p, dp = reset_like_reference(rng, n_a, shapes)
+        params.append(orc.make_params(n_a, grid.shape[1], float(shapes["l_cell"][k]), r_avoid))
+        grids.append(grid); P.append(p); DP.append(dp)
+    return shapes, r_avoid, params, grids, np.stack(P), np.stack(DP)
+
+
+def load_batch(sim, ob, params, grids, P, DP):
+    for e, g in enumerate(grids):
+        ob.set_grid(e, g)
+    ob.p[:], ob.dp[:] = P, DP
+    blocks, n_g = sim.pack_grids(grids, sim.n_g_max)
+    sim.set_grid(blocks, n_g, [p_.l_cell for p_ in params])
+    sim.set_state(P, DP)
+
+
+def compare_all(sim, ob, t, fields=("p", "dp", "obs", "reward", "a_prior", "nbr", "in_flags", "sensed", "occupied")):
+    got = sim_snapshot(sim)
+    ref = dict(p=ob.p, dp=ob.dp, obs=ob.obs, reward=ob.reward, a_prior=ob.a_prior, nbr=ob.neighbor_index,
+               in_flags=ob.in_flags, sensed=ob.sensed_index, occupied=ob.occupied_index)
+    for k in fields:
+        if got[k] is None:
+            continue
+        if not np.array_equal(got[k], ref[k], equal_nan=True):
+            bad = np.argwhere(got[k] != ref[k])
+            raise AssertionError(f"{k} differs at step {t}: {len(bad)} elements, first at {bad[0]} "
+                                 f"got {got[k][tuple(bad[0])]} want {ref[k][tuple(bad[0])]}")
+
+
+@pytest.mark.parametrize("n_a,E,steps,mode", [(30, 256, 200, "mixed"), (30, 64, 200, "goal"), (7, 64, 60, "goal"),
+                                              (33, 32, 60, "goal"), (100, 16, 40, "goal"), (1, 8, 10, "random")])
+def test_batch_vs_oracle_every_step(n_a, E, steps, mode):
+    """Seeded batch, every output of every step compared with the oracle (parity layout: fp64 + index arrays).
+    'goal' drives agents into the shapes so the in-shape / occupancy / 80-cell subsample / reward branches run."""
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=100 + n_a)
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe(with_reward=True)
+    compare_all(sim, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
+    rng = np.random.RandomState(5)
+    in_shape = rewards = 0
+    for t in range(steps):
+        a_rand = rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        a_goal = goal_seeking_action(ob.obs, ob.dp, rng)
+        if mode == "random":
+            a = a_rand
+        elif mode == "goal":
+            a = a_goal
+        else:
+            a = np.where((np.arange(E) % 2 == 0)[:, None, None], a_goal, a_rand)
+        sim.step(torch.from_numpy(a).cuda())
+        ob.step(a)
+        compare_all(sim, ob, t)
+        in_shape += int(ob.in_flags.sum()); rewards += float(ob.reward.sum())
+    if mode != "random" and n_a >= 7:
+        assert in_shape > 0
+    assert not sim.done.any()
+
+
+def test_config2_4096_envs_200_steps():
+    """BASELINE config 2: 30 agents x 4096 envs x 200 steps.  Every env is compared with the oracle at the steps
+    the oracle budget allows (all envs at 10 checkpoints incl. the last, a 128-env slice at every step)."""
+    E, n_a, steps = 4096, 30, 200
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=2)
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    ob = orc.OracleBatch(params, nthreads=16)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe()
+    compare_all(sim, ob, -1, fields=("obs", "nbr", "in_flags", "sensed", "occupied"))
+    act = torch.empty(E, 2, n_a, dtype=torch.float32, device="cuda")
+    rng = np.random.RandomState(9)
+    for t in range(steps):
+        sim.fill_actions(act, seed=226, step=t)
+        a = orc.fill_actions(E, n_a, 226, t)
+        # half the envs follow a noisy goal-seeking controller so shapes get populated
+        a_goal = goal_seeking_action(ob.obs, ob.dp, rng)
+        a = np.where((np.arange(E) % 2 == 1)[:, None, None], a_goal, a)
+        act.copy_(torch.from_numpy(a))
+        sim.step(act)
+        ob.step(a)
+        if t % 20 == 19 or t == steps - 1:
+            compare_all(sim, ob, t)
+        else:
+            got = sim_snapshot(sim, slice(0, 128))
+            assert np.array_equal(got["p"], ob.p[:128]) and np.array_equal(got["obs"], ob.obs[:128]), t
+            assert np.array_equal(got["nbr"], ob.neighbor_index[:128]) and np.array_equal(got["sensed"], ob.sensed_index[:128]), t
+    assert ob.in_flags.sum() > 1000 and ob.reward.sum() > 0
+
+
+def test_fp32_outputs_are_the_rounded_fp64_ones_and_state_stays_fp64():
+    E, n_a = 64, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=31)
+    ngm = int(shapes["n_g"].max())
+    s64 = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    s32 = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32, emit_indices=False)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(s64, ob, params, grids, P, DP)
+    load_batch(s32, ob, params, grids, P, DP)
+    s64.observe(); s32.observe(); ob.observe()
+    rng = np.random.RandomState(1)
+    for t in range(60):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        ta = torch.from_numpy(a).cuda()
+        s64.step(ta); s32.step(ta); ob.step(a)
+        assert torch.equal(s32.p, s64.p) and torch.equal(s32.dp, s64.dp)
+        assert torch.equal(s32.obs, s64.obs.float()) and torch.equal(s32.reward, s64.reward.float())
+        assert torch.equal(s32.a_prior, s64.a_prior.float())
+        assert torch.equal(s32.neighbor_index, s64.neighbor_index) and torch.equal(s32.in_flags, s64.in_flags)
+    assert s32.sensed_index is None and s32.obs.dtype == torch.float32 and s32.p.dtype == torch.float64
+
+
+def test_exact_occupancy_path_equals_shared_mask_path():
+    """The literal per-agent sequential occupancy filter (taken when an agent sits in the rounding shell of the
+    nearby radius) and the shared covered-mask shortcut must give identical lists."""
+    E, n_a = 96, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=77)
+    ngm = int(shapes["n_g"].max())
+    fast = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    slow = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True, exact_occupancy=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(fast, ob, params, grids, P, DP); load_batch(slow, ob, params, grids, P, DP)
+    fast.observe(); slow.observe(); ob.observe()
+    rng = np.random.RandomState(3)
+    for t in range(80):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        ta = torch.from_numpy(a).cuda()
+        fast.step(ta); slow.step(ta); ob.step(a)
+        compare_all(slow, ob, t)
+        for name in ("obs", "reward", "sensed_index", "occupied_index"):
+            assert torch.equal(getattr(fast, name), getattr(slow, name)), (name, t)
+    assert (ob.occupied_index >= 0).sum() > 1000
+
+
+def test_grid_swap_between_steps_like_eval_script():
+    """eval_assembly.py:34-57 overwrites env.grid_center / l_cell / n_g between steps; the next step's prior must come
+    from the NEW grid and the OLD neighbour list (assembly.py:613-624), the observation from the new grid."""
+    E, n_a = 16, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=55)
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    ob = orc.OracleBatch(params, nthreads=4, ng_max=ngm)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe()
+    rng = np.random.RandomState(8)
+    for t in range(30):
+        if t in (10, 20):
+            _, _, params2, grids2, _, _ = build_batch(E, n_a, seed=1000 + t)
+            for e in range(E):
+                ob.params[e].n_g, ob.params[e].l_cell = params2[e].n_g, params2[e].l_cell
+                ob.set_grid(e, grids2[e])
+            blocks, n_g = sim.pack_grids(grids2, ngm)
+            sim.set_grid(blocks, n_g, [p_.l_cell for p_ in params2])
+        if t == 15:   # the caller teleports the agents (env.p = ...): prior uses new p with the stale neighbour list
+            newp = ob.p + rng.normal(0, 0.05, ob.p.shape)
+            ob.p[:] = newp
+            sim.set_state(newp, ob.dp)
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        compare_all(sim, ob, t)
+
+
+def test_step_host_matches_device_step():
+    E, n_a = 32, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=66)
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32)
+    ob = orc.OracleBatch(params, nthreads=4)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe()
+    obs_h = torch.empty(E, 192, n_a, dtype=torch.float32).pin_memory()
+    rew_h = torch.empty(E, 1, n_a, dtype=torch.float32).pin_memory()
+    pri_h = torch.empty(E, 2, n_a, dtype=torch.float32).pin_memory()
+    for t in range(10):
+        a = orc.fill_actions(E, n_a, 4, t)
+        sim.step_host(a, obs_h, rew_h, pri_h)
+        ob.step(a)
+        assert np.array_equal(obs_h.numpy(), ob.obs.astype(np.float32))
+        assert np.array_equal(rew_h.numpy(), ob.reward.astype(np.float32))
+        assert np.array_equal(pri_h.numpy(), ob.a_prior.astype(np.float32))
+
+
+def test_action_generator_matches_oracle():
+    sim = make_sim(128, 30, 64, 0.26)
+    act = torch.empty(128, 2, 30, dtype=torch.float32, device="cuda")
+    sim.fill_actions(act, seed=226, step=17, env_offset=4096)
+    assert np.array_equal(act.cpu().numpy(), orc.fill_actions(128, 30, 226, 17, 4096))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Legacy five-symbol ABI (host pointers), called exactly the way assembly.py calls the reference library.
+# ------------------------------------------------------------------------------------------------------------------
+def _c(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+@pytest.mark.parametrize("n_a", [30, 5, 200])
+def test_legacy_symbols_match_oracle(n_a):
+    from marl_llm_b200 import _lib
+    lib = _lib.load()
+    shapes = load_shapes()
+    rng = np.random.RandomState(n_a)
+    r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    k, grid, p, dp = reset_like_reference(rng, n_a, shapes)
+    # put a third of the agents onto cells so that in-shape branches fire
+    idx = rng.choice(grid.shape[1], n_a // 3 + 1, replace=False)
+    p[:, :len(idx)] = grid[:, idx] + rng.normal(0, 0.01, (2, len(idx)))
+    P = orc.make_params(n_a, grid.shape[1], float(shapes["l_cell"][k]), r_avoid)
+    ob = orc.OracleBatch([P])
+    ob.p[0], ob.dp[0] = p, dp
+    ob.set_grid(0, grid)
+    ob.observe(with_reward=True)
+
+    n_g = grid.shape[1]
+    obs = np.zeros((192, n_a)); nbr = -np.ones((n_a, 6), np.int32); inf = np.zeros(n_a, np.int32)
+    sen = -np.ones((n_a, 80), np.int32); occ = -np.ones((n_a, 200), np.int32)
+    heading = np.zeros((2, n_a)); bp = np.array([-2.4, 2.4, 2.4, -2.4])
+    cond = np.array([False, True, True, False])
+    dbl, i32, bl = C.c_double, C.c_int32, C.c_bool
+    lib._get_observation(_c(p, dbl), _c(dp, dbl), _c(heading, dbl), _c(obs, dbl), _c(bp, dbl), _c(grid, dbl), _c(nbr, i32),
+                         _c(inf, i32), _c(sen, i32), _c(occ, i32), C.c_double(0.4), C.c_double(r_avoid), C.c_double(P.l_cell),
+                         C.c_double(0.8), C.c_int(6), C.c_int(80), C.c_int(200), C.c_int(n_a), C.c_int(n_g), C.c_int(192),
+                         C.c_int(2), _c(cond, bl))
+    assert np.array_equal(obs, ob.obs[0]) and np.array_equal(nbr, ob.neighbor_index[0]) and np.array_equal(inf, ob.in_flags[0])
+    assert np.array_equal(sen, ob.sensed_index[0]) and np.array_equal(occ, ob.occupied_index[0])
+    assert inf.sum() > 0
+
+    rew = np.zeros((1, n_a)); act = np.zeros((2, n_a)); coef = np.array([0.05])
+    cond5 = np.array([False, True, True, True, True])
+    cb2b = np.zeros((n_a, n_a), bool); cb2w = np.zeros((4, n_a), bool)
+    lib._get_reward(_c(p, dbl), _c(dp, dbl), _c(heading, dbl), _c(act, dbl), _c(rew, dbl), _c(bp, dbl), _c(grid, dbl),
+                    _c(nbr, i32), _c(inf, i32), _c(sen, i32), _c(occ, i32), C.c_double(0.4), C.c_double(r_avoid),
+                    C.c_double(P.l_cell), C.c_int(6), C.c_int(80), C.c_int(200), C.c_int(n_a), C.c_int(n_g), C.c_int(2),
+                    _c(cond5, bl), _c(cb2b, bl), _c(cb2w, bl), _c(coef, dbl))
+    assert np.array_equal(rew, ob.reward[0])
+
+    prior = np.zeros((2, n_a))
+    lib.calculateActionPrior(_c(p, dbl), _c(dp, dbl), _c(prior, dbl), _c(grid, dbl), _c(nbr, i32), C.c_double(0.4),
+                             C.c_double(r_avoid), C.c_double(P.l_cell), C.c_int(6), C.c_int(n_a), C.c_int(n_g), C.c_int(2))
+    ref_prior = np.zeros((2, n_a))
+    orc.lib().orc_prior(C.byref(P), _c(p, dbl), _c(dp, dbl), _c(np.ascontiguousarray(grid), dbl), _c(ob.neighbor_index[0], i32),
+                        _c(ref_prior, dbl))
+    assert np.array_equal(prior, ref_prior)
+
+    # NumPy glue of assembly.py:442-457 feeding _sf_b2b_all, and _get_dist_b2w (assembly.py:460-466)
+    pc = p.copy(); pc[:, 1] = pc[:, 0] + np.array([0.03, 0.02]); pc[:, 2] = pc[:, 0] - np.array([0.01, 0.05]) if n_a > 2 else pc[:, 2]
+    pc[0, -1] = 2.39; pc[1, -1] = -2.38
+    all_pos = np.tile(pc, (n_a, 1)); my_pos = np.tile(pc.T.reshape(2 * n_a, 1), (1, n_a))
+    rel = all_pos - my_pos
+    center = np.sqrt(rel[::2] ** 2 + rel[1::2] ** 2)
+    size = np.full(n_a, 0.035); sizes = size[:, None] + size[None, :]; sizes[np.arange(n_a), np.arange(n_a)] = 0
+    edge = center - sizes; coll = edge < 0; edge = np.abs(edge)
+    sf = np.zeros((2, n_a))
+    lib._sf_b2b_all(_c(pc, dbl), _c(sf, dbl), _c(edge, dbl), _c(coll, bl), _c(bp, dbl), _c(center, dbl), C.c_int(n_a), C.c_int(2),
+                    C.c_double(30.0), C.c_bool(False))
+    ref_sf = np.zeros((2, n_a))
+    orc.lib().orc_ball_forces(C.byref(P), _c(pc, dbl), _c(ref_sf, dbl))
+    assert np.array_equal(sf, ref_sf) and np.abs(sf).sum() > 0
+    d_b2w = np.ones((4, n_a)); cw = np.zeros((4, n_a), bool)
+    lib._get_dist_b2w(_c(pc, dbl), _c(size, dbl), _c(d_b2w, dbl), _c(cw, bl), C.c_int(2), C.c_int(n_a), _c(bp, dbl))
+    raw = np.stack([pc[0] - size - bp[0], bp[1] - (pc[1] + size), bp[2] - (pc[0] + size), pc[1] - size - bp[3]])
+    assert np.array_equal(d_b2w, np.abs(raw)) and np.array_equal(cw, raw < 0) and cw.any()

@@ -64,3 +64,24 @@ def test_goal_seeking_exercises_in_shape_branches(seed):
 @pytest.mark.parametrize("n_a,steps", [(1, 20), (2, 50), (10, 100), (64, 60), (200, 10)])
 def test_other_swarm_sizes(n_a, steps):
     rollout_pair(n_a, 11 + n_a, "goal", steps)
+
+
+def test_ref_glue_matches_the_real_env_class():
+    """oracle/ref_glue.RefEnv (restated NumPy glue + the reference's compiled C++) == the real AssemblySwarmEnv,
+    including reset()'s NumPy-global RNG call order.  This is what bench.py --impl reference times on the GPU box."""
+    from oracle import ref_glue
+    from tests.helpers import load_shapes
+    env = lr.make_env(30)
+    glue = ref_glue.RefEnv(30, load_shapes())
+    assert glue.r_avoid == env.env.r_avoid
+    for seed in (226, 5):
+        np.random.seed(seed); o1 = env.reset().copy()
+        np.random.seed(seed); o2 = glue.reset().copy()
+        assert np.array_equal(o1, o2) and np.array_equal(env.env.grid_center, glue.grid_center)
+        rng = np.random.RandomState(seed)
+        for t in range(100):
+            a = goal_seeking_action(env.env.obs, env.env.dp, rng)
+            r1 = env.step(a); r2 = glue.step(a)
+            for x, y in zip((r1[0], r1[1], r1[2], r1[4]), (r2[0], r2[1], r2[2], r2[4])):
+                assert np.array_equal(x, y)
+            assert np.array_equal(env.env.p, glue.p) and np.array_equal(env.env.occupied_index, glue.occupied_index)
