@@ -47,10 +47,12 @@ double thresh_le(double h) {
 
 int round32(int n) { return (n + 31) & ~31; }
 
-size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit) {
+size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
     size_t b = (size_t)n_g_pad * sizeof(double2) + (size_t)4 * nt * sizeof(double);
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 8;
+    b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
+    if (nt == 32 && n_words <= 32) b += (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);   // sparse schedule scratch
     return b;
 }
 
@@ -159,7 +161,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.nbr = buf->neighbor_index; K.in_flags = buf->in_flags; K.nearest = buf->nearest_cell;
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
     s->nt = round32(cfg->n_a);
-    s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0);
+    s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max);
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete s;
         return fail(SWARM_ERR_UNSUPPORTED, "n_a x n_g_max needs more shared memory than one SM has");
@@ -382,7 +384,7 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     if (K.obs_dim != obs_dim_agent) legacy_die(W, "obs_dim_agent does not match 2*2*(6+1+self)+2*num_obs_grid_max");
     K.E = 1;
     const int nt = round32(n_a);
-    const size_t smem = step_smem_bytes(nt, K.n_g_pad, K.n_words, true);
+    const size_t smem = step_smem_bytes(nt, K.n_g_pad, K.n_words, true, num_obs_grid_max);
     const size_t n_obs = (size_t)K.obs_dim * n_a;
     Arena A(al(16 * n_a * 8) + al(2 * n_g * 8) + al(K.n_g_pad * 16) + al(n_obs * 8) + al(n_a * 8 * 3) + al(n_a * TOPO * 4) +
             al(n_a * 8) + al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * num_occupied_grid_max * 4) + 16 * 256, W);
