@@ -212,6 +212,7 @@ def main():
     import torch
     import torch.distributed as dist
     from marl_llm_b200.batched import BatchedAssemblySim, r_avoid_for
+    from marl_llm_b200.sharding import all_reduce_stats, episode_stats, max_over_ranks, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device: the simulator has no CPU fallback")
@@ -232,6 +233,7 @@ def main():
     parity = args.layout == "parity"
     sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, device=local_rank,
                              out_dtype=torch.float64 if parity else torch.float32, emit_indices=parity)
+    env0, _ = shard_range(world * E, rank, world)                       # this rank's global env ids: [env0, env0 + E)
     blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, args.regime)   # shard = own seed = own envs
     sim.set_grid(blocks, n_g, l_cell)
     sim.set_state(p, dp)
@@ -241,7 +243,7 @@ def main():
     ring = min(K + W, 16)
     acts = torch.empty(ring, E, 2, n_a, dtype=torch.float32, device="cuda")
     for r in range(ring):
-        sim.fill_actions(acts[r], seed=226, step=r, env_offset=rank * E)
+        sim.fill_actions(acts[r], seed=226, step=r, env_offset=env0)
     torch.cuda.synchronize()
 
     for t in range(W):
@@ -258,10 +260,8 @@ def main():
     launches = sim.launch_count - l0
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    if world > 1:
-        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+    ms = max_over_ranks(ms, device="cuda")
+    stats = all_reduce_stats(episode_stats(sim.reward, sim.in_flags)).tolist()   # optional episode statistics (not timed)
     value = world * E * n_a * K / (ms * 1e-3)
 
     # ---- roofline of the dominant (only) kernel ----
@@ -299,10 +299,7 @@ def main():
         e1.record()
         barrier()
         ems = e0.elapsed_time(e1)
-        if world > 1:
-            tms = torch.tensor([ems], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ems = float(tms.item())
+        ems = max_over_ranks(ems, device="cuda")
         e2e = {"value": world * E * n_a * K / (ems * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": E * 2 * n_a * 4, "d2h_bytes_per_step": E * n_a * (sim.obs_dim + 1 + 2) * osz,
                "ms_per_step": ems / K, "api": "swarm_step_host (C ABI, pinned host buffers)"}
@@ -332,6 +329,7 @@ def main():
                        "out_dtype": "f64" if parity else "f32", "state_dtype": "f64",
                        "l2": f"working set per step {bytes_per_launch / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                        "actions": f"ring of {ring} pre-generated device buffers"},
+            "last_step_stats": {"mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

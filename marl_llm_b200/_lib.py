@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libswarm_b200.so")
+LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(PKG, "lib", "libswarm_b200.so")   # override: A/B builds
 
 SWARM_OK, SWARM_ERR_INVALID, SWARM_ERR_UNSUPPORTED, SWARM_ERR_CUDA, SWARM_ERR_NO_DEVICE = range(5)
 SWARM_F64, SWARM_F32 = 0, 1

@@ -40,7 +40,8 @@ def build_library(force=False, verbose=False):
     if not (force or is_stale()):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    extra = os.environ.get("SWARM_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)        # the image exports a gcc without libgomp specs
     subprocess.check_call(cmd, env=env)

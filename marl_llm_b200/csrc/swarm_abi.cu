@@ -48,7 +48,7 @@ double thresh_le(double h) {
 int round32(int n) { return (n + 31) & ~31; }
 
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
-    size_t b = (size_t)n_g_pad * sizeof(double2) + (size_t)4 * nt * sizeof(double);
+    size_t b = (SWARM_GRID_GLOBAL ? 0 : (size_t)n_g_pad * sizeof(double2)) + (size_t)4 * nt * sizeof(double);
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 8;
     b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list

@@ -1,0 +1,120 @@
+"""The drop-in mirror of the reference's env class (marl_llm_b200/assembly_env.py + compat/gym) replayed against the golden
+trajectories recorded from the real AssemblySwarmEnv: same seeds -> same reset() (NumPy-global RNG order), same 5-tuples."""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from tests.helpers import GOLDEN_CASES, REPO, load_golden, load_shapes, replay_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def results_blob():
+    sh = load_shapes()
+    return {"l_cell": [float(v) for v in sh["l_cell"]],
+            "grid_coords": [np.ascontiguousarray(g.T) for g in sh["grid_origin"]],
+            "binary_image": [np.zeros((1, 1)) for _ in sh["l_cell"]],
+            "shape_bound_points": [np.zeros(4) for _ in sh["l_cell"]]}
+
+
+def make_args(n_a, **kw):
+    d = dict(n_a=n_a, is_boundary=True, is_con_self_state=True, is_feature_norm=False, dynamics_mode="Cartesian",
+             render_traj=False, traj_len=15, agent_strategy="input", training_method="llm_rl", is_collected=False,
+             results_file=results_blob(), video=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+@pytest.fixture()
+def gym():
+    sys.path.insert(0, os.path.join(REPO, "marl_llm_b200", "compat"))
+    for m in [k for k in sys.modules if k == "gym" or k.startswith("gym.")]:
+        del sys.modules[m]
+    import gym as g
+    assert "swarm_b200" in g.__version__
+    yield g
+    sys.path.remove(os.path.join(REPO, "marl_llm_b200", "compat"))
+    for m in [k for k in sys.modules if k == "gym" or k.startswith("gym.")]:
+        del sys.modules[m]
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_dropin_env_replays_reference_goldens(gym, case):
+    g = load_golden(case)
+    n_a = int(g["n_a"])
+    base = gym.make("AssemblySwarm-v0").unwrapped                     # train_assembly.py:49
+    env = gym.wrappers.AssemblySwarmWrapper(base, make_args(n_a))    # train_assembly.py:50
+    assert env.num_agents == n_a and env.agent_types == ["agent"]
+    assert env.observation_space.shape == (192, n_a) and env.action_space.shape == (2, n_a)
+    assert env.r_avoid == float(g["r_avoid"])
+
+    def snap(obs, rew=None, prior=None):
+        e = env.env
+        return dict(p=e.p, dp=e.dp, obs=obs, reward=rew, a_prior=prior, nbr=e.neighbor_index, in_flags=e.in_flags,
+                    sensed=e.sensed_index, occupied=e.occupied_index)
+
+    def reset_fn(g):
+        np.random.seed(int(g["seed"]))
+        obs = env.reset()
+        assert obs.shape == (192, n_a) and obs.dtype == np.float64
+        assert np.array_equal(env.env.grid_center, g["grid_center"]) and env.env.l_cell == float(g["l_cell"])
+        assert np.array_equal(env.p, g["p0"]) and np.array_equal(env.dp, g["dp0"])
+        return snap(obs)
+
+    def step_fn(a):
+        obs, rew, done, info, prior = env.step(a)
+        assert rew.shape == (1, n_a) and done.shape == (1, n_a) and done.dtype == bool and not done.any()
+        assert info.shape == (3, 1) and prior.shape == (2, n_a)
+        return snap(obs, rew, prior)
+
+    replay_golden(g, reset_fn, step_fn)
+    env.close()
+
+
+def test_eval_script_style_pokes_and_metrics(gym):
+    """eval_assembly.py:34-57 swaps the target shape through env.env.* between steps and reads the wrapper metrics."""
+    from oracle import oracle as orc
+    sh = load_shapes()
+    n_a = 30
+    env = gym.wrappers.AssemblySwarmWrapper(gym.make("AssemblySwarm-v0").unwrapped, make_args(n_a))
+    np.random.seed(3)
+    env.reset()
+    rng = np.random.RandomState(0)
+    for t in range(12):
+        if t == 5:
+            k = 6
+            env.env.l_cell = float(sh["l_cell"][k])
+            env.env.grid_center_origin = sh["grid_origin"][k]
+            env.env.n_g = sh["grid_origin"][k].shape[1]
+            env.env.grid_center = sh["grid_origin"][k].copy() + np.zeros((2, 1))
+        p0, dp0, nbr0 = env.p.copy(), env.dp.copy(), env.env.neighbor_index.copy()
+        a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32)
+        obs, rew, done, info, prior = env.step(a)
+        grid = env.env.grid_center
+        P = orc.make_params(n_a, grid.shape[1], float(env.env.l_cell), env.r_avoid)
+        ob = orc.OracleBatch([P])
+        ob.p[0], ob.dp[0] = p0, dp0
+        ob.set_grid(0, grid)
+        ob.neighbor_index[0] = nbr0
+        ob.step(a[None])
+        assert np.array_equal(obs, ob.obs[0]) and np.array_equal(prior, ob.a_prior[0]) and np.array_equal(rew, ob.reward[0])
+        assert np.array_equal(env.p, ob.p[0])
+    assert 0.0 <= env.coverage_rate() <= 1.0
+    assert np.isfinite(env.distribution_uniformity()) and np.isfinite(env.voronoi_based_uniformity())
+    newp = env.p + 0.01
+    env.env.p = newp                                                 # eval copies / overwrites env.p
+    assert np.array_equal(env.p, newp)
+    env.close()
+
+
+def test_vectorised_variant_has_leading_batch_axis(gym):
+    env = gym.wrappers.AssemblySwarmWrapper(gym.AssemblySwarmEnv(num_envs=4), make_args(30))
+    np.random.seed(1)
+    obs = env.reset()
+    assert obs.shape == (4, 192, 30)
+    out = env.step(np.zeros((4, 2, 30), np.float32))
+    assert out[0].shape == (4, 192, 30) and out[1].shape == (4, 1, 30) and out[4].shape == (4, 2, 30)
+    env.close()
