@@ -48,9 +48,10 @@ double thresh_le(double h) {
 int round32(int n) { return (n + 31) & ~31; }
 
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
-    size_t b = (SWARM_GRID_GLOBAL ? 0 : (size_t)n_g_pad * sizeof(double2)) + (size_t)4 * nt * sizeof(double);
+    (void)n_g_pad;
+    size_t b = (size_t)2 * CHUNK_CELLS * sizeof(double2) + (size_t)4 * nt * sizeof(double);   // TMA ring + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
-    b += (size_t)((n_words + 1) & ~1) * 4 + 8;
+    b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
     b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
     if (nt == 32 && n_words <= 32) b += (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);   // sparse schedule scratch
     return b;

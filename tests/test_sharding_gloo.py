@@ -35,7 +35,9 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_stats_and_timing():
+def test_two_rank_gloo_stats_and_timing(monkeypatch):
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.setenv("PYTHONPATH", repo + os.pathsep + os.environ.get("PYTHONPATH", ""))   # spawned ranks re-import this module
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mgr = mp.Manager()
     out = mgr.dict()
