@@ -87,7 +87,7 @@ def import_reference_gym():
                 name = REF_SO
             super().__init__(name, *a, **k)
 
-    sys.path.insert(0, os.path.join(REF_ROOT, "cus_gym"))
+    sys.path.append(os.path.join(REF_ROOT, "cus_gym"))     # appended: cus_gym/tests must not shadow this repo's tests package
     ctypes.CDLL = _Redirect
     try:
         import gym  # the reference's fork (cus_gym/gym)
