@@ -317,3 +317,26 @@ def test_legacy_symbols_match_oracle(n_a):
     lib._get_dist_b2w(_c(pc, dbl), _c(size, dbl), _c(d_b2w, dbl), _c(cw, bl), C.c_int(2), C.c_int(n_a), _c(bp, dbl))
     raw = np.stack([pc[0] - size - bp[0], bp[1] - (pc[1] + size), bp[2] - (pc[0] + size), pc[1] - size - bp[3]])
     assert np.array_equal(d_b2w, np.abs(raw)) and np.array_equal(cw, raw < 0) and cw.any()
+
+
+def test_large_swarm_1024_agents_matches_oracle():
+    """BASELINE config 4 shape (1024 agents per env, r_avoid = 0.05): the CTA-per-env variant (1024 threads) against the
+    oracle, every output, a few steps (the oracle is O(n_a^2) per env)."""
+    E, n_a = 3, 1024
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=4)
+    assert r_avoid == 0.05
+    rng = np.random.RandomState(12)
+    for e in range(E):      # put a third of each swarm onto the shape so in-shape / occupancy / reward branches run
+        idx = rng.choice(grids[e].shape[1], n_a // 3, replace=False)
+        P[e][:, :n_a // 3] = grids[e][:, idx] + rng.normal(0, 0.01, (2, n_a // 3))
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    ob = orc.OracleBatch(params, nthreads=E)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe(with_reward=True)
+    compare_all(sim, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
+    for t in range(4):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        compare_all(sim, ob, t)
+    assert ob.in_flags.sum() > 100 and (ob.occupied_index >= 0).sum() > 100
