@@ -101,7 +101,7 @@ typedef struct swarm_config {
     int32_t num_obs_grid_max;       /* 80                                              ENV:128          */
     int32_t num_occupied_grid_max;  /* 200                                             ENV:130          */
     int32_t is_con_self_state;      /* obs_dim 192 (1) or 188 (0)                      ENV:107,801      */
-    int32_t is_periodic;            /* 0 only (is_boundary=True, the default)          ENV:99-103       */
+    int32_t is_periodic;            /* !is_boundary: periodic wrap instead of walls     ENV:99-103,651   */
     int32_t want_prior;             /* training_method == 'llm_rl'                     ENV:605          */
     int32_t out_dtype;              /* SWARM_F64 (reference dtype) or SWARM_F32 for obs/reward/a_prior  */
     int32_t emit_indices;           /* also write sensed_index / occupied_index every step             */

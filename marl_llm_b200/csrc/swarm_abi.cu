@@ -70,7 +70,7 @@ step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt) {
 }
 
 void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool self_state, bool want_prior,
-                    bool exact_occ, double d_sen, double r_avoid, double size_a, double k_ball, double k_wall,
+                    bool exact_occ, bool periodic, double d_sen, double r_avoid, double size_a, double k_ball, double k_wall,
                     double c_wall, double dt, double vel_max, double mass, const double *bp) {
     K.n_a = n_a;
     K.n_g_pad = round32(n_g_max);
@@ -81,6 +81,8 @@ void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool
     K.obs_dim = 2 * 2 * (TOPO + 1 + (self_state ? 1 : 0)) + 2 * n_obs;    // ENV:801
     K.want_prior = want_prior;
     K.exact_occ = exact_occ;
+    K.periodic = periodic;
+    K.half_w = (bp[2] - bp[0]) / 2.0; K.half_h = (bp[1] - bp[3]) / 2.0;      // CPP:70-71
     K.d_sen = d_sen; K.r_avoid = r_avoid; K.size_a = size_a; K.two_size = size_a + size_a;   // ENV:785-786
     K.k_ball = k_ball; K.k_wall = k_wall; K.c_wall = c_wall; K.dt = dt; K.vel_max = vel_max; K.mass = mass;
     K.bx_min = bp[0]; K.by_max = bp[1]; K.bx_max = bp[2]; K.by_min = bp[3];
@@ -130,7 +132,6 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     if (cfg->num_envs <= 0 || cfg->n_a <= 0 || cfg->n_g_max <= 0) return fail(SWARM_ERR_INVALID, "sizes must be positive");
     if (cfg->topo_nei_max != TOPO) return fail(SWARM_ERR_UNSUPPORTED, "topo_nei_max must be 6");
     if (cfg->n_a > 1024) return fail(SWARM_ERR_UNSUPPORTED, "n_a > 1024 not supported by the fused kernel");
-    if (cfg->is_periodic) return fail(SWARM_ERR_UNSUPPORTED, "periodic boundaries (is_boundary=False) not implemented");
     if (cfg->num_obs_grid_max < 2 || cfg->num_occupied_grid_max < 2) return fail(SWARM_ERR_INVALID, "list caps must be >= 2");
     if (cfg->out_dtype != SWARM_F64 && cfg->out_dtype != SWARM_F32) return fail(SWARM_ERR_INVALID, "bad out_dtype");
     if (!buf->p || !buf->dp || !buf->grid || !buf->n_g || !buf->in_thresh || !buf->obs || !buf->reward ||
@@ -152,7 +153,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     s->cfg = *cfg; s->buf = *buf;
     memset(&s->K, 0, sizeof(KParams));
     fill_constants(s->K, cfg->n_a, cfg->n_g_max, cfg->num_obs_grid_max, cfg->num_occupied_grid_max,
-                   cfg->is_con_self_state != 0, cfg->want_prior != 0, cfg->exact_occupancy != 0, cfg->d_sen,
+                   cfg->is_con_self_state != 0, cfg->want_prior != 0, cfg->exact_occupancy != 0, cfg->is_periodic != 0, cfg->d_sen,
                    cfg->r_avoid, cfg->size_a, cfg->k_ball, cfg->k_wall, cfg->c_wall, cfg->dt, cfg->vel_max,
                    cfg->mass, cfg->boundary_pos);
     KParams &K = s->K;
@@ -376,12 +377,11 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     const char *W = "_get_observation";
     (void)heading; (void)Vel_max;
     if (dim != 2 || topo_nei_max != TOPO) legacy_die(W, "only dim == 2 and topo_nei_max == 6 are supported");
-    if (condition[0]) legacy_die(W, "periodic boundaries are not implemented");
     if (!condition[1]) legacy_die(W, "only Cartesian dynamics are implemented");
     if (n_a > 1024 || n_a <= 0 || n_g <= 0) legacy_die(W, "n_a must be in [1,1024] and n_g positive");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
     KParams K; memset(&K, 0, sizeof(K));
-    fill_constants(K, n_a, n_g, num_obs_grid_max, num_occupied_grid_max, condition[2], false, false, d_sen, r_avoid,
+    fill_constants(K, n_a, n_g, num_obs_grid_max, num_occupied_grid_max, condition[2], false, false, condition[0], d_sen, r_avoid,
                    0.035, 30.0, 100.0, 5.0, 0.1, 0.8, 1.0, boundary_pos);
     if (K.obs_dim != obs_dim_agent) legacy_die(W, "obs_dim_agent does not match 2*2*(6+1+self)+2*num_obs_grid_max");
     K.E = 1;
@@ -423,10 +423,9 @@ void _get_reward(double *p, double *dp, double *heading, double *act, double *re
                  int num_occupied_grid_max, int n_a, int n_g, int dim, bool *condition, bool *is_collide_b2b,
                  bool *is_collide_b2w, double *coefficients) {
     const char *W = "_get_reward";
-    (void)dp; (void)heading; (void)act; (void)boundary_pos; (void)occupied_index; (void)l_cell;
+    (void)dp; (void)heading; (void)act; (void)occupied_index; (void)l_cell;
     (void)num_occupied_grid_max; (void)is_collide_b2b; (void)is_collide_b2w; (void)coefficients;
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
-    if (condition[0]) legacy_die(W, "periodic boundaries are not implemented");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
     Arena A(al(2 * n_a * 8) + al(2 * (size_t)n_g * 8) + al((size_t)n_a * topo_nei_max * 4) + al(n_a * 4) +
             al((size_t)n_a * num_obs_grid_max * 4) + al(n_a * 8) + 8 * 256, W);
@@ -439,7 +438,8 @@ void _get_reward(double *p, double *dp, double *heading, double *act, double *re
     LEG_TRY(W, cudaMemcpy(d_inf, in_flags, (size_t)n_a * 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_sidx, sensed_index, (size_t)n_a * num_obs_grid_max * 4, cudaMemcpyHostToDevice));
     k_legacy_reward<<<(n_a + 127) / 128, 128>>>(d_p, d_g, d_nbr, d_inf, d_sidx, n_a, n_g, topo_nei_max, num_obs_grid_max,
-                                               d_sen, r_avoid, condition[3], condition[4], d_r);
+                                               d_sen, r_avoid, condition[3], condition[4], condition[0],
+                                               (boundary_pos[2] - boundary_pos[0]) / 2.0, (boundary_pos[1] - boundary_pos[3]) / 2.0, d_r);
     LEG_TRY(W, cudaGetLastError());
     LEG_TRY(W, cudaMemcpy(reward, d_r, (size_t)n_a * 8, cudaMemcpyDeviceToHost));
 }
@@ -447,9 +447,7 @@ void _get_reward(double *p, double *dp, double *heading, double *act, double *re
 void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide_b2b, double *boundary_pos,
                  double *d_b2b_center, int n_a, int dim, double k_ball, bool is_periodic) {
     const char *W = "_sf_b2b_all";
-    (void)boundary_pos;
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
-    if (is_periodic) legacy_die(W, "periodic boundaries are not implemented");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
     const size_t nn = (size_t)n_a * n_a;
     Arena A(al(2 * n_a * 8) * 2 + al(nn * 8) * 2 + al(nn) + 8 * 256, W);
@@ -460,7 +458,8 @@ void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide
     LEG_TRY(W, cudaMemcpy(d_e, d_b2b_edge, nn * 8, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_c, d_b2b_center, nn * 8, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_col, is_collide_b2b, nn, cudaMemcpyHostToDevice));
-    k_legacy_sf_b2b<<<(n_a + 127) / 128, 128>>>(d_p, d_e, d_col, d_c, n_a, k_ball, d_sf);
+    k_legacy_sf_b2b<<<(n_a + 127) / 128, 128>>>(d_p, d_e, d_col, d_c, n_a, k_ball, is_periodic ? 1 : 0,
+                                               (boundary_pos[2] - boundary_pos[0]) / 2.0, (boundary_pos[1] - boundary_pos[3]) / 2.0, d_sf);
     LEG_TRY(W, cudaGetLastError());
     LEG_TRY(W, cudaMemcpy(sf_b2b, d_sf, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
 }

@@ -30,6 +30,7 @@ CASES = [
     ("a30_goal_s3",     30, 3,   "goal",   200, 10),
     ("a10_goal_s15",    10, 15,  "goal",   100, 10),
     ("a64_goal_s75",    64, 75,  "goal",    60, 10),
+    ("a30_periodic_s7", 30, 7,   "drift",  150, 10),   # is_boundary=False: periodic wrap (assembly.py:99-103, 651-652)
 ]
 
 
@@ -38,11 +39,12 @@ def sha(a):
 
 
 def record(n_a, seed, mode, steps, full_every):
-    env = lr.make_env(n_a)
+    periodic = mode == "drift"
+    env = lr.make_env(n_a, is_boundary=not periodic)
     np.random.seed(seed)
     obs0 = env.reset()
     e = env.env
-    out = dict(n_a=n_a, seed=seed, steps=steps, n_g=e.n_g, l_cell=e.l_cell, r_avoid=e.r_avoid, d_sen=e.d_sen,
+    out = dict(n_a=n_a, seed=seed, steps=steps, is_periodic=int(periodic), n_g=e.n_g, l_cell=e.l_cell, r_avoid=e.r_avoid, d_sen=e.d_sen,
                grid_center=e.grid_center.copy(), boundary_pos=e.boundary_pos.copy(),
                p0=e.p.copy(), dp0=e.dp.copy(), obs0=obs0.copy(), nbr0=e.neighbor_index.copy(),
                in_flags0=e.in_flags.copy(), sensed0=e.sensed_index.copy(), occupied0=e.occupied_index.copy())
@@ -50,7 +52,12 @@ def record(n_a, seed, mode, steps, full_every):
     acts, P, DP, R, PR, NB, INF, h_obs, h_sen, h_occ = [], [], [], [], [], [], [], [], [], []
     full_steps, F_obs, F_sen, F_occ = [], [], [], []
     for t in range(steps):
-        a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32) if mode == "random" else goal_seeking_action(e.obs, e.dp, rng)
+        if mode == "random":
+            a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32)
+        elif mode == "drift":      # outward drift: agents cross the box edges and wrap around
+            a = np.clip(0.8 * np.sign(e.p) + rng.normal(0, 0.5, (2, n_a)), -1, 1).astype(np.float32)
+        else:
+            a = goal_seeking_action(e.obs, e.dp, rng)
         obs, rew, done, info, prior = env.step(a)
         assert not done.any() and done.shape == (1, n_a) and done.dtype == bool
         acts.append(a); P.append(e.p.copy()); DP.append(e.dp.copy()); R.append(rew.copy()); PR.append(prior.copy())

@@ -43,7 +43,7 @@ def sha(a):
     return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-GOLDEN_CASES = ["a30_random_s226", "a30_goal_s3", "a10_goal_s15", "a64_goal_s75"]
+GOLDEN_CASES = ["a30_random_s226", "a30_goal_s3", "a10_goal_s15", "a64_goal_s75", "a30_periodic_s7"]
 
 
 def load_golden(name):

@@ -46,7 +46,7 @@ def test_dropin_env_replays_reference_goldens(gym, case):
     g = load_golden(case)
     n_a = int(g["n_a"])
     base = gym.make("AssemblySwarm-v0").unwrapped                     # train_assembly.py:49
-    env = gym.wrappers.AssemblySwarmWrapper(base, make_args(n_a))    # train_assembly.py:50
+    env = gym.wrappers.AssemblySwarmWrapper(base, make_args(n_a, is_boundary=not bool(g.get("is_periodic", 0))))   # train_assembly.py:50
     assert env.num_agents == n_a and env.agent_types == ["agent"]
     assert env.observation_space.shape == (192, n_a) and env.action_space.shape == (2, n_a)
     assert env.r_avoid == float(g["r_avoid"])

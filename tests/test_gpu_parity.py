@@ -31,7 +31,8 @@ def sim_snapshot(sim, e=None):
 def test_golden_trajectories_bit_exact(case):
     g = load_golden(case)
     n_a, n_g = int(g["n_a"]), int(g["n_g"])
-    sim = make_sim(1, n_a, n_g, float(g["r_avoid"]), out_dtype=torch.float64, emit_indices=True, d_sen=float(g["d_sen"]))
+    sim = make_sim(1, n_a, n_g, float(g["r_avoid"]), out_dtype=torch.float64, emit_indices=True, d_sen=float(g["d_sen"]),
+                   is_periodic=bool(g.get("is_periodic", 0)))
 
     def reset_fn(g):
         blocks, ng = sim.pack_grids([g["grid_center"]], n_g)
@@ -340,3 +341,28 @@ def test_large_swarm_1024_agents_matches_oracle():
         sim.step(torch.from_numpy(a).cuda()); ob.step(a)
         compare_all(sim, ob, t)
     assert ob.in_flags.sum() > 100 and (ob.occupied_index >= 0).sum() > 100
+
+
+def test_periodic_boundaries_batch_vs_oracle():
+    """is_boundary=False: wrap of relative positions in k-NN / obs / reward and of p after the
+    integrator, no wall forces.  The oracle's periodic mode is pinned to the live reference in the build container."""
+    E, n_a = 64, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=91)
+    for p_ in params:
+        p_.is_periodic = 1
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True, is_periodic=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe(with_reward=True)
+    compare_all(sim, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
+    rng = np.random.RandomState(2)
+    wrapped = 0
+    for t in range(120):
+        drift = np.clip(0.8 * np.sign(ob.p) + rng.normal(0, 0.5, ob.p.shape), -1, 1).astype(np.float32)
+        a = np.where((np.arange(E) % 2 == 0)[:, None, None], drift, goal_seeking_action(ob.obs, ob.dp, rng))
+        before = ob.p.copy()
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        wrapped += int((np.abs(ob.p - before) > 2.0).sum())
+        compare_all(sim, ob, t)
+    assert wrapped > 100

@@ -10,7 +10,8 @@ from tests.helpers import GOLDEN_CASES, load_golden, replay_golden
 
 def oracle_impl(g):
     n_a = int(g["n_a"])
-    P = orc.make_params(n_a, int(g["n_g"]), float(g["l_cell"]), float(g["r_avoid"]), d_sen=float(g["d_sen"]))
+    P = orc.make_params(n_a, int(g["n_g"]), float(g["l_cell"]), float(g["r_avoid"]), d_sen=float(g["d_sen"]),
+                        is_periodic=bool(g.get("is_periodic", 0)))
     ob = orc.OracleBatch([P])
 
     def snapshot():

@@ -85,3 +85,35 @@ def test_ref_glue_matches_the_real_env_class():
             for x, y in zip((r1[0], r1[1], r1[2], r1[4]), (r2[0], r2[1], r2[2], r2[4])):
                 assert np.array_equal(x, y)
             assert np.array_equal(env.env.p, glue.p) and np.array_equal(env.env.occupied_index, glue.occupied_index)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_periodic_boundaries_match_reference(seed):
+    """is_boundary=False -> periodic wrap (assembly.py:99-103, 447-448, 651-652; AssemblyEnv.cpp:88-90, 474-477, 700-732),
+    including the reference's quirk that _get_dist_b2b only wraps agent 0's rows."""
+    n_a = 30
+    env = lr.make_env(n_a, is_boundary=False)
+    np.random.seed(seed)
+    env.reset()
+    e = env.env
+    assert e.is_periodic
+    P = orc.make_params(n_a, e.n_g, float(e.l_cell), float(e.r_avoid), is_periodic=True)
+    ob = orc.OracleBatch([P])
+    ob.p[0], ob.dp[0] = e.p, e.dp
+    ob.set_grid(0, e.grid_center)
+    ob.observe()
+    assert np.array_equal(ob.obs[0], e.obs) and np.array_equal(ob.neighbor_index[0], e.neighbor_index)
+    rng = np.random.RandomState(seed)
+    wrapped = 0
+    for t in range(150):
+        # outward drift so that agents cross the box edges and wrap
+        a = np.clip(0.8 * np.sign(e.p) + rng.normal(0, 0.5, (2, n_a)), -1, 1).astype(np.float32)
+        before = e.p.copy()
+        obs, rew, done, info, prior = env.step(a)
+        ob.step(a[None])
+        wrapped += int((np.abs(e.p - before) > 2.0).sum())
+        for name, x, y in (("p", ob.p[0], e.p), ("dp", ob.dp[0], e.dp), ("obs", ob.obs[0], obs), ("rew", ob.reward[0], rew),
+                           ("prior", ob.a_prior[0], prior), ("nbr", ob.neighbor_index[0], e.neighbor_index),
+                           ("sen", ob.sensed_index[0], e.sensed_index), ("occ", ob.occupied_index[0], e.occupied_index)):
+            assert np.array_equal(x, y, equal_nan=True), f"{name} differs at step {t}"
+    assert wrapped > 10
