@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--layout", default="production", choices=["production", "parity"],
                     help="production: fp64 state, fp32 obs/reward/prior; parity: everything fp64 + index arrays")
     ap.add_argument("--regime", default="random", choices=["random", "converged"])
+    ap.add_argument("--brute-force-scan", action="store_true", help="A/B: disable the word-box culling of the grid scan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
@@ -232,7 +233,8 @@ def main():
     r_avoid = r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
     parity = args.layout == "parity"
     sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, device=local_rank,
-                             out_dtype=torch.float64 if parity else torch.float32, emit_indices=parity)
+                             out_dtype=torch.float64 if parity else torch.float32, emit_indices=parity,
+                             brute_force_scan=args.brute_force_scan)
     env0, _ = shard_range(world * E, rank, world)                       # this rank's global env ids: [env0, env0 + E)
     blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, args.regime)   # shard = own seed = own envs
     sim.set_grid(blocks, n_g, l_cell)

@@ -106,6 +106,8 @@ typedef struct swarm_config {
     int32_t out_dtype;              /* SWARM_F64 (reference dtype) or SWARM_F32 for obs/reward/a_prior  */
     int32_t emit_indices;           /* also write sensed_index / occupied_index every step             */
     int32_t exact_occupancy;        /* debug: always take the per-agent sequential occupancy filter    */
+    int32_t brute_force_scan;       /* debug / A-B: evaluate every (agent, cell) pair in the grid scan    */
+    int32_t reserved_;
     double d_sen;                   /* 0.4                                             ENV:199          */
     double r_avoid;                 /*                                                 ENV:124          */
     double size_a;                  /* 0.035                                           ENV:44           */
@@ -124,13 +126,16 @@ typedef struct swarm_buffers {
     double *grid;              /* [E][n_g_pad][2]        internal cell-major copy of grid_center, written by
                                   swarm_set_grid; n_g_pad = swarm_grid_pad(n_g_max)                      */
     int32_t *n_g;              /* [E]                    written by swarm_set_grid                         */
+    float *word_box;           /* [E][n_g_pad/32][4]     written by swarm_set_grid: bounding box of every 32-cell word    */
+    double *frame;             /* [E][2]                 written by swarm_set_grid: unit axis of the env's box frame      */
     double *in_thresh;         /* [E]                    written by swarm_set_grid (in-shape threshold)    */
     void *obs;                 /* [E][obs_dim][n_a] OUT  ENV:227, layout CPP:324-328                       */
     void *reward;              /* [E][1][n_a]       OUT  ENV:353                                           */
     void *a_prior[2];          /* 2 x [E][2][n_a]   OUT  ENV:612; double-buffered, see swarm_a_prior_ptr   */
     int32_t *neighbor_index;   /* [E][n_a][6]            ENV:228                                           */
     int32_t *in_flags;         /* [E][n_a]               ENV:229                                           */
-    int32_t *nearest_cell;     /* [E][n_a]               index of the nearest cell (CPP:884-885)           */
+    int32_t *nearest_cell;     /* [E][n_a]               index of the nearest cell (CPP:884-885); also the seed of the
+                                                         next step's nearest-cell search (any content is a valid seed) */
     int32_t *sensed_index;     /* [E][n_a][80]           ENV:230   (may be NULL unless emit_indices)       */
     int32_t *occupied_index;   /* [E][n_a][200]          ENV:231   (may be NULL unless emit_indices)       */
 } swarm_buffers;

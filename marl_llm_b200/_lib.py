@@ -16,7 +16,7 @@ class SwarmConfig(C.Structure):
         ("n_g_max", C.c_int32), ("topo_nei_max", C.c_int32), ("num_obs_grid_max", C.c_int32),
         ("num_occupied_grid_max", C.c_int32), ("is_con_self_state", C.c_int32), ("is_periodic", C.c_int32),
         ("want_prior", C.c_int32), ("out_dtype", C.c_int32), ("emit_indices", C.c_int32),
-        ("exact_occupancy", C.c_int32),
+        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("reserved_", C.c_int32),
         ("d_sen", C.c_double), ("r_avoid", C.c_double), ("size_a", C.c_double),
         ("k_ball", C.c_double), ("k_wall", C.c_double), ("c_wall", C.c_double),
         ("dt", C.c_double), ("vel_max", C.c_double), ("mass", C.c_double),
@@ -28,6 +28,7 @@ class SwarmBuffers(C.Structure):
     _fields_ = [
         ("struct_size", C.c_int32), ("pad_", C.c_int32),
         ("p", C.c_void_p), ("dp", C.c_void_p), ("grid", C.c_void_p), ("n_g", C.c_void_p),
+        ("word_box", C.c_void_p), ("frame", C.c_void_p),
         ("in_thresh", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
         ("a_prior", C.c_void_p * 2),
         ("neighbor_index", C.c_void_p), ("in_flags", C.c_void_p), ("nearest_cell", C.c_void_p),

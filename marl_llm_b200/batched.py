@@ -35,7 +35,7 @@ class BatchedAssemblySim:
     def __init__(self, num_envs, n_a, n_g_max, r_avoid, *, device=0, out_dtype=torch.float32, emit_indices=False,
                  want_prior=True, is_con_self_state=True, is_periodic=False, d_sen=0.4, size_a=0.035, k_ball=30.0,
                  k_wall=100.0, c_wall=5.0, dt=0.1, vel_max=0.8, mass=1.0, half_width=2.4, half_height=2.4,
-                 exact_occupancy=False):
+                 exact_occupancy=False, brute_force_scan=False):
         if not torch.cuda.is_available():
             raise SwarmError("BatchedAssemblySim needs a CUDA device; there is no CPU fallback")
         if out_dtype not in (torch.float32, torch.float64):
@@ -56,6 +56,7 @@ class BatchedAssemblySim:
         cfg.is_con_self_state, cfg.is_periodic, cfg.want_prior = int(is_con_self_state), int(is_periodic), int(want_prior)
         cfg.out_dtype = _lib.SWARM_F32 if out_dtype == torch.float32 else _lib.SWARM_F64
         cfg.emit_indices, cfg.exact_occupancy = int(emit_indices), int(exact_occupancy)
+        cfg.brute_force_scan = int(brute_force_scan)
         cfg.d_sen, cfg.r_avoid, cfg.size_a = d_sen, r_avoid, size_a
         cfg.k_ball, cfg.k_wall, cfg.c_wall = k_ball, k_wall, c_wall
         cfg.dt, cfg.vel_max, cfg.mass = dt, vel_max, mass
@@ -71,6 +72,9 @@ class BatchedAssemblySim:
         self._grid = z(E, self.n_g_pad, 2, dtype=torch.float64)
         self._n_g = z(E, dtype=torch.int32)
         self._in_thresh = z(E, dtype=torch.float64)
+        self._word_box = z(E, self.n_g_pad // 32, 4, dtype=torch.float32)    # acceleration data of the culled grid scan
+        self._frame = z(E, 2, dtype=torch.float64)
+        self.nearest_cell = z(E, n, dtype=torch.int32)
         self.obs = z(E, self.obs_dim, n, dtype=out_dtype)
         self.reward = z(E, 1, n, dtype=out_dtype)
         self.done = z(E, 1, n, dtype=torch.bool)
@@ -78,21 +82,21 @@ class BatchedAssemblySim:
         self.neighbor_index = torch.full((E, n, TOPO_NEI_MAX), -1, dtype=torch.int32, device=dev)
         self.in_flags = z(E, n, dtype=torch.int32)
         if emit_indices:
-            self.nearest_cell = z(E, n, dtype=torch.int32)
             self.sensed_index = torch.full((E, n, NUM_OBS_GRID_MAX), -1, dtype=torch.int32, device=dev)
             self.occupied_index = torch.full((E, n, NUM_OCC_GRID_MAX), -1, dtype=torch.int32, device=dev)
         else:
-            self.nearest_cell = self.sensed_index = self.occupied_index = None
+            self.sensed_index = self.occupied_index = None
 
         buf = SwarmBuffers()
         buf.struct_size = C.sizeof(SwarmBuffers)
         buf.p, buf.dp, buf.grid = self.p.data_ptr(), self.dp.data_ptr(), self._grid.data_ptr()
         buf.n_g, buf.in_thresh = self._n_g.data_ptr(), self._in_thresh.data_ptr()
+        buf.word_box, buf.frame = self._word_box.data_ptr(), self._frame.data_ptr()
+        buf.nearest_cell = self.nearest_cell.data_ptr()
         buf.obs, buf.reward = self.obs.data_ptr(), self.reward.data_ptr()
         buf.a_prior[0], buf.a_prior[1] = self._a_prior[0].data_ptr(), self._a_prior[1].data_ptr()
         buf.neighbor_index, buf.in_flags = self.neighbor_index.data_ptr(), self.in_flags.data_ptr()
         if emit_indices:
-            buf.nearest_cell = self.nearest_cell.data_ptr()
             buf.sensed_index, buf.occupied_index = self.sensed_index.data_ptr(), self.occupied_index.data_ptr()
         self._buf = buf
         h = C.c_void_p()
@@ -227,7 +231,8 @@ class BatchedAssemblySim:
         b += osz                       # write reward
         b += (2 * osz if self.want_prior else 0)       # write next prior
         b += TOPO_NEI_MAX * 4 + 4      # write neighbor_index + in_flags
+        b += 4 + 4                     # read + write nearest_cell (seed of the nearest-cell search)
         b += 2 * 8 * math.ceil(ng / 32) * 32 / self.n_a   # read the env's cell list once per env
         if self.emit_indices:
-            b += (NUM_OBS_GRID_MAX + NUM_OCC_GRID_MAX + 1) * 4
+            b += (NUM_OBS_GRID_MAX + NUM_OCC_GRID_MAX) * 4
         return b

@@ -49,7 +49,7 @@ int round32(int n) { return (n + 31) & ~31; }
 
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
     (void)n_g_pad;
-    size_t b = (size_t)2 * CHUNK_CELLS * sizeof(double2) + (size_t)4 * nt * sizeof(double);   // TMA ring + state tile
+    size_t b = (size_t)2 * CHUNK_CELLS * sizeof(double2) + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
     b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
@@ -93,6 +93,7 @@ void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool
     K.T_near_hi = (d_near * (1.0 + 1e-9)) * (d_near * (1.0 + 1e-9));
     K.U_occ = thresh_le(r_avoid / 2.0);                                   // CPP:185
     K.T_avoid = thresh_lt(r_avoid);                                       // CPP:482, 1166
+    K.Tsen_f = std::nextafterf((float)(K.T_sen * 1.01 + 1e-4), INFINITY);   // box test threshold, deliberately loose
 }
 
 double in_shape_thresh(double l_cell) { return thresh_lt(std::sqrt(2.0) * l_cell / 2); }   // CPP:889
@@ -135,10 +136,11 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     if (cfg->num_obs_grid_max < 2 || cfg->num_occupied_grid_max < 2) return fail(SWARM_ERR_INVALID, "list caps must be >= 2");
     if (cfg->out_dtype != SWARM_F64 && cfg->out_dtype != SWARM_F32) return fail(SWARM_ERR_INVALID, "bad out_dtype");
     if (!buf->p || !buf->dp || !buf->grid || !buf->n_g || !buf->in_thresh || !buf->obs || !buf->reward ||
-        !buf->a_prior[0] || !buf->a_prior[1] || !buf->neighbor_index || !buf->in_flags)
+        !buf->a_prior[0] || !buf->a_prior[1] || !buf->neighbor_index || !buf->in_flags || !buf->word_box || !buf->frame ||
+        !buf->nearest_cell)
         return fail(SWARM_ERR_INVALID, "required device buffer is NULL");
-    if (cfg->emit_indices && (!buf->sensed_index || !buf->occupied_index || !buf->nearest_cell))
-        return fail(SWARM_ERR_INVALID, "emit_indices needs sensed_index / occupied_index / nearest_cell buffers");
+    if (cfg->emit_indices && (!buf->sensed_index || !buf->occupied_index))
+        return fail(SWARM_ERR_INVALID, "emit_indices needs sensed_index / occupied_index buffers");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -160,6 +162,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.E = cfg->num_envs;
     K.p = buf->p; K.dp = buf->dp; K.grid = reinterpret_cast<const double2 *>(buf->grid);
     K.n_g = buf->n_g; K.in_thresh = buf->in_thresh;
+    K.wbox = reinterpret_cast<const float4 *>(buf->word_box); K.frame = buf->frame; K.brute_scan = cfg->brute_force_scan != 0;
     K.obs = buf->obs; K.reward = buf->reward;
     K.nbr = buf->neighbor_index; K.in_flags = buf->in_flags; K.nearest = buf->nearest_cell;
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
@@ -216,7 +219,9 @@ int swarm_set_grid(swarm_sim *s, int32_t env0, int32_t count, const double *grid
         src = s->d_stage;
     }
     k_pack_grid<<<count, 128, 0, st>>>(src, (long)2 * ngm, s->buf.n_g + env0, s->K.n_g_pad,
-                                       reinterpret_cast<double2 *>(s->buf.grid) + (size_t)env0 * s->K.n_g_pad);
+                                       reinterpret_cast<double2 *>(s->buf.grid) + (size_t)env0 * s->K.n_g_pad,
+                                       reinterpret_cast<float4 *>(s->buf.word_box) + (size_t)env0 * s->K.n_words,
+                                       s->buf.frame + (size_t)env0 * 2);
     CU_TRY(cudaGetLastError());
     s->launches++;
     // thr/n_g host vectors must outlive the async copies
@@ -388,11 +393,12 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     const int nt = round32(n_a);
     const size_t smem = step_smem_bytes(nt, K.n_g_pad, K.n_words, true, num_obs_grid_max);
     const size_t n_obs = (size_t)K.obs_dim * n_a;
-    Arena A(al(16 * n_a * 8) + al(2 * n_g * 8) + al(K.n_g_pad * 16) + al(n_obs * 8) + al(n_a * 8 * 3) + al(n_a * TOPO * 4) +
+    Arena A(al(16 * n_a * 8) + al(2 * n_g * 8) + al(K.n_g_pad * 16) + al(K.n_words * 16) + al(16) + al(n_obs * 8) + al(n_a * 8 * 3) + al(n_a * TOPO * 4) +
             al(n_a * 8) + al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * num_occupied_grid_max * 4) + 16 * 256, W);
     double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_gsrc = A.take<double>(2 * n_g);
     double2 *d_grid = A.take<double2>(K.n_g_pad);
     int *d_ng = A.take<int>(1); double *d_thr = A.take<double>(1);
+    float4 *d_box = A.take<float4>(K.n_words); double *d_frame = A.take<double>(2);
     double *d_obs = A.take<double>(n_obs), *d_rew = A.take<double>(n_a), *d_prior = A.take<double>(2 * n_a);
     int *d_nbr = A.take<int>(n_a * TOPO), *d_inf = A.take<int>(n_a), *d_near = A.take<int>(n_a);
     int *d_sidx = A.take<int>((size_t)n_a * num_obs_grid_max), *d_occ = A.take<int>((size_t)n_a * num_occupied_grid_max);
@@ -402,7 +408,9 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid);
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid, d_box, d_frame);
+    LEG_TRY(W, cudaMemset(d_near, 0, (size_t)n_a * 4));
+    K.wbox = d_box; K.frame = d_frame;
     K.p = d_p; K.dp = d_dp; K.grid = d_grid; K.n_g = d_ng; K.in_thresh = d_thr;
     K.obs = d_obs; K.reward = d_rew; K.prior_next = d_prior;
     K.nbr = d_nbr; K.in_flags = d_inf; K.nearest = d_near; K.sensed = d_sidx; K.occupied = d_occ;
@@ -487,12 +495,14 @@ void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_c
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
     const int n_g_pad = round32(n_g);
-    Arena A(al(2 * n_a * 8) * 3 + al(2 * (size_t)n_g * 8) + al((size_t)n_g_pad * 16) + al((size_t)n_a * topo_nei_max * 4) + 10 * 256, W);
+    Arena A(al(2 * n_a * 8) * 3 + al(2 * (size_t)n_g * 8) + al((size_t)n_g_pad * 16) + al((size_t)n_g_pad / 2) + al(16) +
+            al((size_t)n_a * topo_nei_max * 4) + 12 * 256, W);
     double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_out = A.take<double>(2 * n_a);
     double *d_gsrc = A.take<double>(2 * (size_t)n_g);
     double2 *d_grid = A.take<double2>(n_g_pad);
     int *d_nbr = A.take<int>((size_t)n_a * topo_nei_max), *d_ng = A.take<int>(1);
     double *d_thr = A.take<double>(1);
+    float4 *d_box = A.take<float4>(n_g_pad / 32); double *d_frame = A.take<double>(2);
     const double thr = in_shape_thresh(l_cell);
     LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_dp, dp, 2 * n_a * 8, cudaMemcpyHostToDevice));
@@ -500,7 +510,7 @@ void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_c
     LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid);
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid, d_box, d_frame);
     k_prior<double><<<1, n_a < 256 ? round32(n_a) : 256>>>(n_a, topo_nei_max, d_p, d_dp, d_grid, n_g_pad, d_ng, d_thr, d_nbr, r_avoid, d_out);
     LEG_TRY(W, cudaGetLastError());
     LEG_TRY(W, cudaMemcpy(a_prior, d_out, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));

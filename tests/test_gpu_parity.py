@@ -366,3 +366,29 @@ def test_periodic_boundaries_batch_vs_oracle():
         wrapped += int((np.abs(ob.p - before) > 2.0).sum())
         compare_all(sim, ob, t)
     assert wrapped > 100
+
+
+@pytest.mark.parametrize("n_a", [30, 100])
+def test_culled_scan_equals_brute_force_scan_and_ignores_seed_content(n_a):
+    """The word-box culled grid scan (default) against the all-pairs scan and the oracle, with the nearest-cell seed buffer
+    deliberately filled with garbage before some steps (any content must be a valid seed)."""
+    E = 48
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=500 + n_a)
+    ngm = int(shapes["n_g"].max())
+    fast = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    brute = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True, brute_force_scan=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(fast, ob, params, grids, P, DP); load_batch(brute, ob, params, grids, P, DP)
+    fast.nearest_cell.random_(-5, 5000)                       # garbage seeds, including out-of-range ones
+    fast.observe(); brute.observe(); ob.observe()
+    rng = np.random.RandomState(6)
+    for t in range(60):
+        a = np.where((np.arange(E) % 2 == 0)[:, None, None], goal_seeking_action(ob.obs, ob.dp, rng),
+                     rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32))
+        if t % 7 == 3:
+            fast.nearest_cell.random_(-5, 5000)
+        ta = torch.from_numpy(a).cuda()
+        fast.step(ta); brute.step(ta); ob.step(a)
+        compare_all(fast, ob, t)
+        for name in ("obs", "reward", "sensed_index", "occupied_index", "nearest_cell", "in_flags"):
+            assert torch.equal(getattr(fast, name), getattr(brute, name)), (name, t)
