@@ -313,8 +313,10 @@ def main():
         cores = os.cpu_count() or 1
         if ref_glue.available():
             r = ref_glue.timed_rollouts(n_a, shapes, cores, 2, 200)
+            r1 = ref_glue.timed_rollouts(n_a, shapes, 1, 1, 200)          # BASELINE config 1: one env, one core, 200 steps
             cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"{cores} processes x 2 episodes x 200 steps x {n_a} agents (reference C++ via oracle/_ref + NumPy glue)"}
+                   "sample": f"{cores} processes x 2 episodes x 200 steps x {n_a} agents (reference C++ via oracle/_ref + NumPy glue)",
+                   "single_core_value": r1["value"]}
         else:
             from oracle import oracle as orc
             r = port_rollouts(orc, shapes, n_a, cores, 64 * cores, 50)
@@ -326,9 +328,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"assembly env, {n_a} agents x {E} envs per GPU, env-sharded (BASELINE config 3)",
+            "config": {"workload": (f"assembly env, {n_a} agents x {E} envs per GPU, env-sharded (BASELINE config 3)" if n_a == 30 else
+                                    f"large swarm: {n_a} agents x {E} envs per GPU (BASELINE config 4)"),
                        "n_a": n_a, "envs_per_gpu": E, "layout": args.layout, "regime": args.regime,
                        "out_dtype": "f64" if parity else "f32", "state_dtype": "f64",
+                       "grid_scan": "all-pairs" if args.brute_force_scan else "word-box culled",
                        "l2": f"working set per step {bytes_per_launch / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                        "actions": f"ring of {ring} pre-generated device buffers"},
             "last_step_stats": {"mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]},
