@@ -93,7 +93,7 @@ void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool
     K.T_near_hi = (d_near * (1.0 + 1e-9)) * (d_near * (1.0 + 1e-9));
     K.U_occ = thresh_le(r_avoid / 2.0);                                   // CPP:185
     K.T_avoid = thresh_lt(r_avoid);                                       // CPP:482, 1166
-    K.Tsen_f = std::nextafterf((float)(K.T_sen * 1.01 + 1e-4), INFINITY);   // box test threshold, deliberately loose
+    K.Tsen_f = std::nextafterf((float)(K.T_sen * (double)SLACK_REL + (double)SLACK_ABS), INFINITY);   // box test threshold
 }
 
 double in_shape_thresh(double l_cell) { return thresh_lt(std::sqrt(2.0) * l_cell / 2); }   // CPP:889
