@@ -155,6 +155,19 @@ int swarm_destroy(swarm_sim *sim);
 int swarm_set_grid(swarm_sim *sim, int32_t env0, int32_t count, const double *grid, int grid_on_device,
                    const int32_t *n_g, const double *l_cell, void *stream);
 
+/* Device-resident shape library for swarm_reset(): n_shapes blocks of 2*n_g_max doubles (host), each holding a shape's
+ * origin-frame grid [2][n_g] (the transposed `grid_coords` of the reference's results.pkl, ENV:117,164), with its cell
+ * count and cell size (ENV:116,163). */
+int swarm_set_shapes(swarm_sim *sim, int32_t n_shapes, const double *grids, const int32_t *n_g, const double *l_cell);
+
+/* reset() on the device, ENV:156-223: shape pick, rotation, offset, initial positions and velocities for every env (or
+ * those with env_mask[e] != 0; device pointer or NULL), then the observation of the new state (ENV:221).  Random draws come
+ * from a counter-based generator keyed by (seed, episode, env_offset + e), not from NumPy's global stream; the map from the
+ * draws to grid_center / p / dp is the reference's.  info_dev (device, [E][8] f64, may be NULL) receives per env
+ * {shape index, cos, sin, offset_x, offset_y, wide-spawn flag, 0, 0}. */
+int swarm_reset(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
+                double *info_dev, void *stream);
+
 /* Tell the handle that the caller overwrote p / dp (device buffers) outside step(): the next step recomputes the
  * prior from the new state and the stale neighbor_index, exactly like the reference would (ENV:613-624). */
 int swarm_mark_state_dirty(swarm_sim *sim);

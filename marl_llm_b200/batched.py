@@ -153,6 +153,29 @@ class BatchedAssemblySim:
             n_g[k] = g.shape[1]
         return out, n_g
 
+    def set_shapes(self, grid_origins, l_cells):
+        """Upload the shape library used by reset(): grid_origins is a list of [2, n_g] origin-frame grids (the transposed
+        `grid_coords` of the reference's results.pkl, assembly.py:117,164), l_cells their cell sizes."""
+        blocks, n_g = self.pack_grids(grid_origins, self.n_g_max)
+        l_cells = np.ascontiguousarray(l_cells, dtype=np.float64)
+        check(self.lib.swarm_set_shapes(self._h, len(grid_origins), C.c_void_p(blocks.ctypes.data), C.c_void_p(n_g.ctypes.data),
+                                        C.c_void_p(l_cells.ctypes.data)), "swarm_set_shapes")
+        self.shape_l_cells, self.shape_n_g = l_cells.copy(), n_g.copy()
+
+    def reset(self, seed, episode=0, env_offset=0, env_mask=None):
+        """reset() of assembly.py:156-223 for all envs (or those where env_mask is True) on the device, then the first
+        observation.  Returns obs; `self.reset_info` [E, 8] holds {shape, cos, sin, off_x, off_y, wide-spawn flag, 0, 0}."""
+        if not hasattr(self, "reset_info"):
+            self.reset_info = torch.zeros(self.E, 8, dtype=torch.float64, device=self.device)
+        mptr = None
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            assert env_mask.numel() == self.E
+            mptr = C.c_void_p(env_mask.data_ptr())
+        check(self.lib.swarm_reset(self._h, int(seed), int(episode), int(env_offset), mptr,
+                                   C.c_void_p(self.reset_info.data_ptr()), self._stream()), "swarm_reset")
+        return self.obs
+
     def set_state(self, p, dp):
         """Overwrite positions / velocities ([E,2,n_a]); like assigning env.p / env.dp in the reference."""
         self.p.copy_(torch.as_tensor(p, dtype=torch.float64).reshape(self.E, 2, self.n_a))

@@ -113,6 +113,8 @@ struct swarm_sim {
     int64_t launches;
     double *d_stage; size_t stage_cap;     // set_grid staging (reference-layout grid)
     float *d_act; size_t act_cap;          // step_host action staging
+    double *d_shape_grid; int *d_shape_ng; double *d_shape_thr; int n_shapes;   // swarm_set_shapes
+    std::vector<double> shape_l_cell;
 };
 
 extern "C" {
@@ -179,6 +181,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     }
     s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
     s->d_stage = nullptr; s->stage_cap = 0; s->d_act = nullptr; s->act_cap = 0;
+    s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
     *out = s;
     return SWARM_OK;
 }
@@ -188,6 +191,9 @@ int swarm_destroy(swarm_sim *s) {
     cudaSetDevice(s->cfg.device);
     if (s->d_stage) cudaFree(s->d_stage);
     if (s->d_act) cudaFree(s->d_act);
+    if (s->d_shape_grid) cudaFree(s->d_shape_grid);
+    if (s->d_shape_ng) cudaFree(s->d_shape_ng);
+    if (s->d_shape_thr) cudaFree(s->d_shape_thr);
     delete s;
     return SWARM_OK;
 }
@@ -228,6 +234,48 @@ int swarm_set_grid(swarm_sim *s, int32_t env0, int32_t count, const double *grid
     CU_TRY(cudaStreamSynchronize(st));
     s->prior_dirty = true;
     return SWARM_OK;
+}
+
+int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const int32_t *n_g, const double *l_cell) {
+    if (!s || !grids || !n_g || !l_cell || n_shapes <= 0) return fail(SWARM_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const int ngm = s->cfg.n_g_max;
+    std::vector<double> thr(n_shapes);
+    for (int k = 0; k < n_shapes; ++k) {
+        if (n_g[k] <= 0 || n_g[k] > ngm) return fail(SWARM_ERR_INVALID, "shape n_g out of range (0, n_g_max]");
+        thr[k] = in_shape_thresh(l_cell[k]);
+    }
+    if (s->d_shape_grid) { cudaFree(s->d_shape_grid); cudaFree(s->d_shape_ng); cudaFree(s->d_shape_thr); }
+    s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
+    CU_TRY(cudaMalloc(&s->d_shape_grid, sizeof(double) * (size_t)n_shapes * 2 * ngm));
+    CU_TRY(cudaMalloc(&s->d_shape_ng, sizeof(int) * n_shapes));
+    CU_TRY(cudaMalloc(&s->d_shape_thr, sizeof(double) * n_shapes));
+    CU_TRY(cudaMemcpy(s->d_shape_grid, grids, sizeof(double) * (size_t)n_shapes * 2 * ngm, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(s->d_shape_ng, n_g, sizeof(int) * n_shapes, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(s->d_shape_thr, thr.data(), sizeof(double) * n_shapes, cudaMemcpyHostToDevice));
+    s->n_shapes = n_shapes;
+    s->shape_l_cell.assign(l_cell, l_cell + n_shapes);
+    return SWARM_OK;
+}
+
+int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
+                double *info_dev, void *stream) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    if (s->n_shapes <= 0) return fail(SWARM_ERR_INVALID, "swarm_reset before swarm_set_shapes");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    ResetParams R;
+    R.n_a = s->cfg.n_a; R.n_g_pad = s->K.n_g_pad; R.n_g_cap = s->cfg.n_g_max; R.n_shapes = s->n_shapes;
+    R.half_w = s->K.half_w; R.half_h = s->K.half_h;
+    R.shape_grid = s->d_shape_grid; R.shape_n_g = s->d_shape_ng; R.shape_thresh = s->d_shape_thr;
+    R.p = s->buf.p; R.dp = s->buf.dp; R.grid = reinterpret_cast<double2 *>(s->buf.grid); R.n_g = s->buf.n_g;
+    R.in_thresh = s->buf.in_thresh; R.wbox = reinterpret_cast<float4 *>(s->buf.word_box); R.frame = s->buf.frame;
+    R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = env_mask;
+    R.seed = seed; R.episode = episode; R.env_offset = env_offset;
+    k_reset<<<s->cfg.num_envs, 128, 0, (cudaStream_t)stream>>>(R);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    s->prior_dirty = true;
+    return swarm_observe(s, stream);     // ENV:221; a masked reset re-observes every env (idempotent for the untouched ones)
 }
 
 int swarm_mark_state_dirty(swarm_sim *s) {
