@@ -168,6 +168,10 @@ int swarm_set_shapes(swarm_sim *sim, int32_t n_shapes, const double *grids, cons
 int swarm_reset(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
                 double *info_dev, void *stream);
 
+/* Evaluation metrics of the reference wrapper for every env, on the device: out_dev [E][3] f64 =
+ * {coverage_rate, distribution_uniformity, voronoi_based_uniformity} (assembly_wrapper.py:48-72, 74-101, 103-129). */
+int swarm_metrics(swarm_sim *sim, double *out_dev, void *stream);
+
 /* Tell the handle that the caller overwrote p / dp (device buffers) outside step(): the next step recomputes the
  * prior from the new state and the stale neighbor_index, exactly like the reference would (ENV:613-624). */
 int swarm_mark_state_dirty(swarm_sim *sim);

@@ -252,7 +252,7 @@ class Agent:
 
 class AssemblySwarmWrapper:
     """WRAP:18-129: re-inits the env with `args`, exposes num_agents/agents/agent_types and the three eval metrics
-    (host-side NumPy restatements; they are not on the step path)."""
+    (computed on the device by `k_metrics`; they are not on the step path)."""
 
     def __init__(self, env, args):
         self.env = env
@@ -283,19 +283,18 @@ class AssemblySwarmWrapper:
     def close(self):
         return self.env.close()
 
-    def coverage_rate(self):                           # WRAP:48-72
-        p, g = self.env.p, self.env.grid_center
-        d = np.linalg.norm(p[:, None, :] - g[:, :, None], axis=0)        # [n_g, n_a]
-        return float((d < self.env.r_avoid / 2).any(axis=1).sum() / g.shape[1])
+    def _metric(self, k):
+        env = self.env
+        if env._grid_dirty:
+            env._push_grid()
+        m = env._sim.metrics()[:, k].cpu().numpy()
+        return float(m[0]) if env.num_envs == 1 else m
+
+    def coverage_rate(self):                           # WRAP:48-72, on the device (swarm_metrics)
+        return self._metric(0)
 
     def distribution_uniformity(self):                 # WRAP:74-101
-        p = self.env.p
-        d = np.linalg.norm(p[:, None, :] - p[:, :, None], axis=0)
-        mins = np.array([row[row != 0].min() for row in d])
-        return float((np.var(mins) - mins.min()) / (mins.max() - mins.min()))
+        return self._metric(1)
 
     def voronoi_based_uniformity(self):                # WRAP:103-129
-        p, g = self.env.p, self.env.grid_center
-        d = np.linalg.norm(p[:, None, :] - g[:, :, None], axis=0)        # [n_g, n_a]
-        counts = np.bincount(np.argmin(d, axis=1), minlength=p.shape[1]).astype(float)
-        return float((np.var(counts) - counts.min()) / (counts.max() - counts.min()))
+        return self._metric(2)

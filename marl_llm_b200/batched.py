@@ -176,6 +176,14 @@ class BatchedAssemblySim:
                                    C.c_void_p(self.reset_info.data_ptr()), self._stream()), "swarm_reset")
         return self.obs
 
+    def metrics(self):
+        """[E, 3] float64 device tensor: coverage_rate, distribution_uniformity, voronoi_based_uniformity of every env
+        (assembly_wrapper.py:48-129), computed on the device."""
+        if not hasattr(self, "_metrics"):
+            self._metrics = torch.zeros(self.E, 3, dtype=torch.float64, device=self.device)
+        check(self.lib.swarm_metrics(self._h, C.c_void_p(self._metrics.data_ptr()), self._stream()), "swarm_metrics")
+        return self._metrics
+
     def set_state(self, p, dp):
         """Overwrite positions / velocities ([E,2,n_a]); like assigning env.p / env.dp in the reference."""
         self.p.copy_(torch.as_tensor(p, dtype=torch.float64).reshape(self.E, 2, self.n_a))

@@ -278,6 +278,18 @@ int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offs
     return swarm_observe(s, stream);     // ENV:221; a masked reset re-observes every env (idempotent for the untouched ones)
 }
 
+int swarm_metrics(swarm_sim *s, double *out_dev, void *stream) {
+    if (!s || !out_dev) return fail(SWARM_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const int n_a = s->cfg.n_a;
+    const size_t smem = (size_t)3 * n_a * sizeof(double) + (size_t)(n_a + 2) * sizeof(int);
+    k_metrics<<<s->cfg.num_envs, 128, smem, (cudaStream_t)stream>>>(n_a, s->K.p, s->K.grid, s->K.n_g_pad, s->K.n_g,
+                                                                    thresh_lt(s->cfg.r_avoid / 2), out_dev);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    return SWARM_OK;
+}
+
 int swarm_mark_state_dirty(swarm_sim *s) {
     if (!s) return fail(SWARM_ERR_INVALID, "null handle");
     s->prior_dirty = true;

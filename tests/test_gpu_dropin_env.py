@@ -118,3 +118,34 @@ def test_vectorised_variant_has_leading_batch_axis(gym):
     out = env.step(np.zeros((4, 2, 30), np.float32))
     assert out[0].shape == (4, 192, 30) and out[1].shape == (4, 1, 30) and out[4].shape == (4, 2, 30)
     env.close()
+
+
+def test_wrapper_metrics_match_the_reference_formulas(gym):
+    """coverage_rate / distribution_uniformity / voronoi_based_uniformity (assembly_wrapper.py:48-129) computed on the device
+    against a NumPy restatement of the reference loops."""
+    n_a = 30
+    env = gym.wrappers.AssemblySwarmWrapper(gym.make("AssemblySwarm-v0").unwrapped, make_args(n_a))
+    np.random.seed(11)
+    env.reset()
+    rng = np.random.RandomState(1)
+    from tests.helpers import goal_seeking_action
+    for t in range(60):
+        env.step(goal_seeking_action(env.env.obs, env.dp, rng))
+        if t % 20 != 19:
+            continue
+        p, g, r = env.p, env.env.grid_center, env.r_avoid
+        occupied = sum(1 for c in range(g.shape[1]) if (np.linalg.norm(p - g[:, [c]], axis=0) < r / 2).any())   # WRAP:59-66
+        assert env.coverage_rate() == occupied / g.shape[1]
+        mins = []
+        for i in range(n_a):                                                                                   # WRAP:87-95
+            d = np.linalg.norm(p - p[:, [i]], axis=0)
+            mins.append(np.min(d[d != 0]))
+        ref2 = (np.var(mins) - np.min(mins)) / (np.max(mins) - np.min(mins))
+        assert abs(env.distribution_uniformity() - ref2) <= 1e-12 * max(1.0, abs(ref2))
+        cnt = np.zeros(n_a)
+        for c in range(g.shape[1]):                                                                            # WRAP:114-121
+            cnt[np.argmin(np.linalg.norm(p - g[:, [c]], axis=0))] += 1
+        ref3 = (np.var(cnt) - np.min(cnt)) / (np.max(cnt) - np.min(cnt))
+        assert abs(env.voronoi_based_uniformity() - ref3) <= 1e-12 * max(1.0, abs(ref3))
+    assert occupied > 0
+    env.close()
