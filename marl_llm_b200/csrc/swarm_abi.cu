@@ -53,7 +53,8 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
     b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
-    if (nt == 32 && n_words <= 32) b += (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);   // sparse schedule scratch
+    const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
+    if (nt == 32 && n_words <= 32 && scratch > (size_t)2 * CHUNK_CELLS * sizeof(double2)) b += scratch;   // aliases the TMA ring when it fits
     return b;
 }
 
@@ -170,6 +171,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
     s->nt = round32(cfg->n_a);
     s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max);
+    if (const char *x = getenv("SWARM_DEBUG_EXTRA_SMEM")) s->smem += (size_t)atoi(x);   // occupancy experiments only
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete s;
         return fail(SWARM_ERR_UNSUPPORTED, "n_a x n_g_max needs more shared memory than one SM has");

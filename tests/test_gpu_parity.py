@@ -392,3 +392,41 @@ def test_culled_scan_equals_brute_force_scan_and_ignores_seed_content(n_a):
         compare_all(fast, ob, t)
         for name in ("obs", "reward", "sensed_index", "occupied_index", "nearest_cell", "in_flags"):
             assert torch.equal(getattr(fast, name), getattr(brute, name)), (name, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("emit", [False, True])
+def test_every_output_element_is_rewritten_each_step(emit):
+    """The observation buffer is poisoned before every step (NaN / garbage indices): every element must be rewritten.
+    Guards the zero-fill + speculative in-scan emission of the sensed-cell rows (stale slots when an agent enters the
+    shape, loses cells to the occupancy filter, or crosses the 80-cell subsample threshold).  Production layout
+    (fp32, no index arrays) and parity layout, mixed random / goal-seeking envs, compared with the oracle every step."""
+    E, n_a, steps = 192, 30, 150
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=77)
+    ngm = int(shapes["n_g"].max())
+    dt = torch.float64 if emit else torch.float32
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.obs.fill_(float("nan"))
+    sim.observe(); ob.observe()
+    cast = np.float64 if emit else np.float32
+    assert np.array_equal(sim.obs.cpu().numpy(), ob.obs.astype(cast))
+    rng = np.random.RandomState(3)
+    for t in range(steps):
+        a_rand = rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        a_goal = goal_seeking_action(ob.obs, ob.dp, rng)
+        a = np.where((np.arange(E) % 3 != 0)[:, None, None], a_goal, a_rand)
+        sim.obs.fill_(float("nan")); sim.reward.fill_(float("nan"))
+        if emit:
+            sim.sensed_index.fill_(-7); sim.occupied_index.fill_(-7); sim.neighbor_index.fill_(-7)
+        sim.step(torch.from_numpy(a).cuda())
+        ob.step(a)
+        assert np.array_equal(sim.obs.cpu().numpy(), ob.obs.astype(cast)), t
+        assert np.array_equal(sim.reward.cpu().numpy(), ob.reward.astype(cast)), t
+        assert np.array_equal(sim.a_prior.cpu().numpy(), ob.a_prior.astype(cast)), t
+        assert np.array_equal(sim.neighbor_index.cpu().numpy(), ob.neighbor_index), t
+        if emit:
+            assert np.array_equal(sim.sensed_index.cpu().numpy(), ob.sensed_index), t
+            assert np.array_equal(sim.occupied_index.cpu().numpy(), ob.occupied_index), t
+    assert ob.in_flags.sum() > 100 and ob.reward.sum() > 0
