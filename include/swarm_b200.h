@@ -204,6 +204,31 @@ int swarm_kernel_geometry(const swarm_sim *sim, int32_t *threads_per_cta, int32_
  * distances with these instead of taking square roots. */
 double swarm_sqrt_threshold(double d, int le);
 
+/* ============================================================================================
+ * (3) Device-resident replay storage — replaces the host NumPy ring of
+ *     marl_llm/algorithm/utils/buffer_agent.py (= BUF) for the batched simulator.  Stateless: the caller owns the ring
+ *     arrays (device, f32, row-major [capacity][dim]) and the write cursor; the host mirror
+ *     (marl_llm_b200/rollout.py:ReplayBufferAgent) keeps curr_i / filled_i exactly like BUF:96-127.
+ * ============================================================================================ */
+typedef struct swarm_rollout_buffers {
+    int32_t struct_size, obs_dim, act_dim, pad_;
+    int64_t capacity;                 /* rows = max_steps * num_agents (BUF:46) */
+    float *obs, *act, *act_prior, *log_pi, *rew, *next_obs, *done;   /* BUF:49-55; act_prior / log_pi may be NULL */
+} swarm_rollout_buffers;
+
+/* push(), BUF:67-128, for num_envs envs at once: the simulator's feature-major arrays (obs / next_obs [E][obs_dim][n_a],
+ * reward [E][1][n_a], act_prior [E][act_dim][n_a] in out_dtype; act [E][act_dim][n_a] in act_dtype; done [E][1][n_a] bool;
+ * log_pi [E][1][n_a] f32 or NULL) are transposed to agent rows (BUF:86-90, agents [agent_start, agent_stop) of every env,
+ * env-major) and written to ring rows [row0, row0 + E*(agent_stop-agent_start)). */
+int swarm_rollout_push(const swarm_rollout_buffers *buf, int64_t row0, int32_t num_envs, int32_t n_a, int32_t agent_start,
+                       int32_t agent_stop, const void *obs, const void *next_obs, const void *reward, const uint8_t *done,
+                       const void *act_prior, int out_dtype, const void *act, int act_dtype, const float *log_pi, void *stream);
+
+/* the gather of sample(), BUF:152-161: rows_dev [n] int64 ring rows (device) -> [n][dim] f32 outputs (device);
+ * act_prior / log_pi outputs may be NULL (BUF:159-162 is_prior / is_log_pi). */
+int swarm_rollout_gather(const swarm_rollout_buffers *buf, const int64_t *rows_dev, int32_t n, float *obs, float *act, float *reward,
+                         float *next_obs, float *done, float *act_prior, float *log_pi, void *stream);
+
 const char *swarm_last_error(void);
 int swarm_abi_version(void);
 

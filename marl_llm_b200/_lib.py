@@ -43,6 +43,16 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold"]
+ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
+
+
+class SwarmRolloutBuffers(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("pad_", C.c_int32),
+        ("capacity", C.c_int64),
+        ("obs", C.c_void_p), ("act", C.c_void_p), ("act_prior", C.c_void_p), ("log_pi", C.c_void_p),
+        ("rew", C.c_void_p), ("next_obs", C.c_void_p), ("done", C.c_void_p),
+    ]
 
 _lib = None
 
@@ -79,6 +89,10 @@ def load():
     lib.swarm_kernel_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.swarm_grid_pad.argtypes = [C.c_int32]
     lib.swarm_obs_dim.argtypes = [C.POINTER(SwarmConfig)]
+    lib.swarm_rollout_push.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_void_p]
+    lib.swarm_rollout_gather.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_void_p, C.c_int32] + [C.c_void_p] * 8
     lib.swarm_sqrt_threshold.restype = C.c_double
     lib.swarm_sqrt_threshold.argtypes = [C.c_double, C.c_int]
     _lib = lib

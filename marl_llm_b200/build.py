@@ -8,7 +8,8 @@ import subprocess
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc", "swarm_abi.cu")
-DEPS = [SRC, os.path.join(PKG, "csrc", "swarm_kernels.cuh"),
+SRCS = [SRC, os.path.join(PKG, "csrc", "rollout_abi.cu")]
+DEPS = SRCS + [os.path.join(PKG, "csrc", "swarm_kernels.cuh"), os.path.join(PKG, "csrc", "rollout_kernels.cuh"),
         os.path.join(os.path.dirname(PKG), "include", "swarm_b200.h")]
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libswarm_b200.so")
@@ -41,7 +42,7 @@ def build_library(force=False, verbose=False):
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
     extra = os.environ.get("SWARM_NVCC_EXTRA", "").split()
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SRCS
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)        # the image exports a gcc without libgomp specs
     subprocess.check_call(cmd, env=env)

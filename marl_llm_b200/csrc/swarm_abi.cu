@@ -120,6 +120,9 @@ struct swarm_sim {
 
 extern "C" {
 
+/* shared with the other translation units of the library */
+int swarm_set_last_error_(int code, const char *msg) { return fail(code, msg); }
+
 int swarm_abi_version(void) { return 1; }
 /* host-only helper exposed for tests: the squared-distance threshold equivalent to sqrt(s) < d (le=0) or <= d (le=1) */
 double swarm_sqrt_threshold(double d, int le) { return le ? thresh_le(d) : thresh_lt(d); }

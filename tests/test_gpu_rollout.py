@@ -1,0 +1,80 @@
+"""Device-resident replay storage (C ABI group 3 + marl_llm_b200/rollout.py) against the oracle restatement of the
+reference's ReplayBufferAgent: ring contents, cursor arithmetic (step-back + wrap) and seeded sample() batches."""
+import numpy as np
+import pytest
+import torch
+
+from marl_llm_b200.rollout import ReplayBufferAgent
+from oracle.replay_oracle import ReplayOracle
+
+pytestmark = pytest.mark.gpu
+
+ARRAYS = ("obs_buffs", "ac_buffs", "ac_prior_buffs", "rew_buffs", "next_obs_buffs", "done_buffs", "log_pi_buffs")
+
+
+def assert_same(dev, orc):
+    for name in ARRAYS:
+        assert np.array_equal(getattr(dev, name).cpu().numpy(), getattr(orc, name).astype(np.float32)), name
+    assert (dev.curr_i, dev.filled_i, len(dev)) == (orc.curr_i, orc.filled_i, len(orc))
+
+
+@pytest.mark.parametrize("n_a,D", [(30, 192), (7, 188), (100, 192), (1, 16)])
+def test_reference_shaped_host_pushes_rollover_and_seeded_samples(n_a, D):
+    A = 2
+    max_steps = 300200 // n_a + 3
+    idx = slice(0, n_a)
+    dev, orc = ReplayBufferAgent(max_steps, n_a, idx, D, A), ReplayOracle(max_steps, n_a, idx, D, A)
+    rng = np.random.RandomState(n_a)
+    for b in (dev, orc):
+        b.curr_i = b.filled_i = b.total_length - 2 * n_a - min(3, n_a - 1) - 1
+    for t in range(5):
+        obs, nxt = rng.randn(D, n_a), rng.randn(D, n_a)                          # fp64, like the reference env
+        act = rng.uniform(-1, 1, (A, n_a)).astype(np.float32)                     # TRAIN:99 column_stack of fp32
+        prior, rew, done = rng.uniform(-1, 1, (A, n_a)), rng.rand(1, n_a), rng.rand(1, n_a) > 0.5
+        logpi = rng.randn(1, n_a).astype(np.float32) if t % 2 else None
+        dev.push(obs, act, rew, nxt, done, idx, prior, logpi)
+        orc.push(obs, act, rew, nxt, done, idx, prior, logpi)
+        assert_same(dev, orc)
+    for seed in (1, 2):
+        np.random.seed(seed); got = dev.sample(128, to_gpu=True, is_prior=True, is_log_pi=True)
+        np.random.seed(seed); want, _ = orc.sample(128, is_prior=True, is_log_pi=True)
+        for a, b in zip(got, want):
+            assert a.is_cuda and np.array_equal(a.cpu().numpy(), b)
+    np.random.seed(3); host = dev.sample(16)
+    assert host[5] is None and host[6] is None and not host[0].is_cuda and host[0].dtype == torch.float32
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.float64])
+def test_batched_device_push_from_simulator_layout(out_dtype):
+    E, n_a, D, A = 37, 30, 192, 2
+    idx = slice(0, n_a)
+    dev, orc = ReplayBufferAgent(40, E * n_a, idx, D, A), ReplayOracle(40, E * n_a, idx, D, A)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(45):                                                           # > max_steps: wraps to row 0
+        obs = torch.randn(E, D, n_a, device="cuda", generator=g).to(out_dtype)
+        nxt = torch.randn(E, D, n_a, device="cuda", generator=g).to(out_dtype)
+        act = torch.rand(E, A, n_a, device="cuda", generator=g) * 2 - 1
+        prior = (torch.rand(E, A, n_a, device="cuda", generator=g) * 2 - 1).to(out_dtype)
+        rew = torch.rand(E, 1, n_a, device="cuda", generator=g).to(out_dtype)
+        done = torch.rand(E, 1, n_a, device="cuda", generator=g) > 0.7
+        dev.push(obs, act, rew, nxt, done, idx, prior)
+        orc.push(*(x.cpu().numpy() for x in (obs, act, rew, nxt, done)), idx, prior.cpu().numpy())
+    assert_same(dev, orc)
+    rows = np.random.RandomState(0).randint(0, dev.total_length, 300)
+    got = dev.gather(rows, is_prior=True)
+    assert np.array_equal(got[0].cpu().numpy(), orc.obs_buffs[rows].astype(np.float32))
+    assert np.array_equal(got[3].cpu().numpy(), orc.next_obs_buffs[rows].astype(np.float32))
+    assert np.array_equal(got[5].cpu().numpy(), orc.ac_prior_buffs[rows].astype(np.float32))
+
+
+def test_agent_slice_and_errors():
+    n_a, D, A = 12, 20, 2
+    dev, orc = ReplayBufferAgent(50, 5, slice(3, 8), D, A), ReplayOracle(50, 5, slice(3, 8), D, A)
+    rng = np.random.RandomState(2)
+    for t in range(4):
+        obs, nxt, act = rng.randn(D, n_a), rng.randn(D, n_a), rng.randn(A, n_a).astype(np.float32)
+        rew, done = rng.rand(1, n_a), rng.rand(1, n_a) > 0.5
+        dev.push(obs, act, rew, nxt, done, slice(3, 8)); orc.push(obs, act, rew, nxt, done, slice(3, 8))
+    assert_same(dev, orc)
+    with pytest.raises(IndexError):
+        dev.gather([dev.total_length])
