@@ -229,6 +229,28 @@ int swarm_rollout_push(const swarm_rollout_buffers *buf, int64_t row0, int32_t n
 int swarm_rollout_gather(const swarm_rollout_buffers *buf, const int64_t *rows_dev, int32_t n, float *obs, float *act, float *reward,
                          float *next_obs, float *done, float *act_prior, float *log_pi, void *stream);
 
+/* ============================================================================================
+ * (4) Rollout policy on the device: MADDPG.step() of marl_llm/algorithm/algorithms/maddpg.py:72-87
+ *     (DDPGAgent.step, utils/agents.py:69-96; MLPNetwork.forward, utils/networks.py:33-44) for every agent of every env,
+ *     reading the simulator's obs layout and writing its action layout.  fp32 FFMA, fp32 accumulation.
+ * ============================================================================================ */
+typedef struct swarm_policy swarm_policy;
+
+/* obs_dim, hidden_dim <= 192 (reference: 192, 180), act_dim <= 8 (reference: 2). */
+int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int32_t act_dim, swarm_policy **out);
+int swarm_policy_destroy(swarm_policy *p);
+/* HOST pointers, torch nn.Linear layout: w1 [hidden][obs_dim], w2, w3 [hidden][hidden], w4 [act_dim][hidden], biases [out]
+ * (networks.py:22-25 fc1..fc4). */
+int swarm_policy_load(swarm_policy *p, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                      const float *b3, const float *w4, const float *b4);
+/* obs: DEVICE [E][obs_dim][n_a] f32 -> act: DEVICE [E][act_dim][n_a] f32 = tanh(fc4(lrelu(fc3(lrelu(fc2(lrelu(fc1 obs))))))).
+ * explore (agents.py:85-93): 0 none; 1 act += noise_scale * N(0,1), clamp to [-1,1]; 2 act = U(-1,1) (the epsilon branch; the
+ * caller draws epsilon once per step like the reference).  Noise comes from a counter-based generator keyed by
+ * (seed, step, column, component), not from NumPy.  log_pi: DEVICE [E][1][n_a] f32 or NULL (agents.py:82,88,91). */
+int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32_t n_a, float *act, float *log_pi, int explore,
+                      float noise_scale, uint64_t seed, uint64_t step, void *stream);
+int64_t swarm_policy_launch_count(const swarm_policy *p);
+
 const char *swarm_last_error(void);
 int swarm_abi_version(void);
 

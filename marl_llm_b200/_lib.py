@@ -44,6 +44,7 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold"]
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
+POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count"]
 
 
 class SwarmRolloutBuffers(C.Structure):
@@ -93,6 +94,13 @@ def load():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p]
     lib.swarm_rollout_gather.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+    lib.swarm_policy_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.swarm_policy_destroy.argtypes = [C.c_void_p]
+    lib.swarm_policy_load.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    lib.swarm_policy_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                                      C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.swarm_policy_launch_count.restype = C.c_int64
+    lib.swarm_policy_launch_count.argtypes = [C.c_void_p]
     lib.swarm_sqrt_threshold.restype = C.c_double
     lib.swarm_sqrt_threshold.argtypes = [C.c_double, C.c_int]
     _lib = lib

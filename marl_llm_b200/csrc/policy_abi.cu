@@ -1,0 +1,109 @@
+// policy_abi.cu — C ABI of the on-device rollout policy (include/swarm_b200.h, group 4).  No CPU implementation.
+#include "policy_kernels.cuh"
+#include "../../include/swarm_b200.h"
+
+#include <string>
+#include <vector>
+
+using namespace swarm;
+
+extern "C" int swarm_set_last_error_(int code, const char *msg);   // swarm_abi.cu
+
+namespace {
+int pfail(int code, const std::string &m) { return swarm_set_last_error_(code, m.c_str()); }
+#define PCU_TRY(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t err__ = (expr);                                                                     \
+        if (err__ != cudaSuccess) return pfail(SWARM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+constexpr size_t POL_SMEM = ((size_t)2 * POL_HP * POL_M + (size_t)2 * POL_KC * POL_HP) * sizeof(float);
+}  // namespace
+
+struct swarm_policy {
+    int device, obs_dim, hidden, act_dim;
+    float *d_w;          // one allocation: Wt[3][HP][HP], b[3][HP], W4[A][HP], b4[A]
+    bool loaded;
+    int64_t launches;
+};
+
+extern "C" {
+
+int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int32_t act_dim, swarm_policy **out) {
+    if (!out) return pfail(SWARM_ERR_INVALID, "null argument");
+    if (obs_dim <= 0 || obs_dim > POL_HP || hidden_dim <= 0 || hidden_dim > POL_HP || act_dim <= 0 || act_dim > POL_AMAX)
+        return pfail(SWARM_ERR_UNSUPPORTED, "policy sizes: obs_dim, hidden_dim <= 192, act_dim <= 8");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return pfail(SWARM_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return pfail(SWARM_ERR_INVALID, "device ordinal out of range");
+    PCU_TRY(cudaSetDevice(device));
+    swarm_policy *p = new swarm_policy();
+    p->device = device; p->obs_dim = obs_dim; p->hidden = hidden_dim; p->act_dim = act_dim; p->loaded = false; p->launches = 0;
+    const size_t n = (size_t)3 * POL_HP * POL_HP + 3 * POL_HP + (size_t)act_dim * POL_HP + act_dim;
+    cudaError_t e = cudaMalloc(&p->d_w, n * sizeof(float));
+    if (e != cudaSuccess) { delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
+    if (e != cudaSuccess) { cudaFree(p->d_w); delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    *out = p;
+    return SWARM_OK;
+}
+
+int swarm_policy_destroy(swarm_policy *p) {
+    if (!p) return SWARM_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_w);
+    delete p;
+    return SWARM_OK;
+}
+
+int swarm_policy_load(swarm_policy *p, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
+                      const float *b3, const float *w4, const float *b4) {
+    if (!p || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !w4 || !b4) return pfail(SWARM_ERR_INVALID, "null argument");
+    PCU_TRY(cudaSetDevice(p->device));
+    const int H = p->hidden, K0 = p->obs_dim, A = p->act_dim;
+    const size_t n = (size_t)3 * POL_HP * POL_HP + 3 * POL_HP + (size_t)A * POL_HP + A;
+    std::vector<float> h(n, 0.f);
+    const float *W[3] = {w1, w2, w3}, *B[3] = {b1, b2, b3};
+    const int Kin[3] = {K0, H, H};
+    for (int l = 0; l < 3; ++l) {
+        float *wt = h.data() + (size_t)l * POL_HP * POL_HP;                       // Wt[k][n] = W[n][k] (torch Linear.weight is [out][in])
+        for (int nn = 0; nn < H; ++nn)
+            for (int k = 0; k < Kin[l]; ++k) wt[(size_t)k * POL_HP + nn] = W[l][(size_t)nn * Kin[l] + k];
+        float *bb = h.data() + (size_t)3 * POL_HP * POL_HP + (size_t)l * POL_HP;
+        for (int nn = 0; nn < H; ++nn) bb[nn] = B[l][nn];
+    }
+    float *w4p = h.data() + (size_t)3 * POL_HP * POL_HP + 3 * POL_HP;
+    for (int j = 0; j < A; ++j)
+        for (int k = 0; k < H; ++k) w4p[(size_t)j * POL_HP + k] = w4[(size_t)j * H + k];
+    for (int j = 0; j < A; ++j) w4p[(size_t)A * POL_HP + j] = b4[j];
+    PCU_TRY(cudaMemcpy(p->d_w, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    p->loaded = true;
+    return SWARM_OK;
+}
+
+int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32_t n_a, float *act, float *log_pi, int explore,
+                      float noise_scale, uint64_t seed, uint64_t step, void *stream) {
+    if (!p || !obs || !act) return pfail(SWARM_ERR_INVALID, "null argument");
+    if (!p->loaded) return pfail(SWARM_ERR_INVALID, "swarm_policy_step before swarm_policy_load");
+    if (num_envs <= 0 || n_a <= 0 || explore < 0 || explore > 2) return pfail(SWARM_ERR_INVALID, "bad argument");
+    PCU_TRY(cudaSetDevice(p->device));
+    PolicyParams P;
+    P.obs = obs; P.act = act; P.log_pi = log_pi;
+    P.n_cols = (long)num_envs * n_a; P.n_a = n_a; P.K0 = p->obs_dim; P.A = p->act_dim;
+    for (int l = 0; l < 3; ++l) {
+        P.Wt[l] = p->d_w + (size_t)l * POL_HP * POL_HP;
+        P.b[l] = p->d_w + (size_t)3 * POL_HP * POL_HP + (size_t)l * POL_HP;
+    }
+    P.W4 = p->d_w + (size_t)3 * POL_HP * POL_HP + 3 * POL_HP;
+    P.b4 = P.W4 + (size_t)p->act_dim * POL_HP;
+    P.slope = 0.01f; P.explore = explore; P.scale = noise_scale; P.seed = seed; P.step = step;
+    const long ctas = (P.n_cols + POL_M - 1) / POL_M;
+    k_policy_mlp<<<(unsigned)ctas, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(P);
+    PCU_TRY(cudaGetLastError());
+    p->launches++;
+    return SWARM_OK;
+}
+
+int64_t swarm_policy_launch_count(const swarm_policy *p) { return p ? p->launches : 0; }
+
+}  // extern "C"

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert set(_lib.LEGACY_SYMBOLS) <= set(syms) and len(syms) >= 20
     for s in syms:
         assert getattr(lib, s) is not None, s
-    assert set(syms) == set(_lib.LEGACY_SYMBOLS + _lib.BATCHED_SYMBOLS + _lib.ROLLOUT_SYMBOLS)
+    assert set(syms) == set(_lib.LEGACY_SYMBOLS + _lib.BATCHED_SYMBOLS + _lib.ROLLOUT_SYMBOLS + _lib.POLICY_SYMBOLS)
 
 
 def test_legacy_alias_name_exists():

@@ -1,0 +1,71 @@
+"""On-device rollout policy (C ABI group 4) against a plain torch fp32 restatement of the reference network
+(marl_llm/algorithm/utils/networks.py:22-44: four nn.Linear, F.leaky_relu, tanh output) and of DDPGAgent.step's
+exploration (utils/agents.py:82-93, utils/noise.py:24-37).  Floating point: rtol 1e-5 / atol 2e-6 (fp32 sums in a
+different order than torch's GEMM; the north star's tolerance for floating point is 1e-5 relative)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from marl_llm_b200.policy import DevicePolicy
+
+pytestmark = pytest.mark.gpu
+
+
+class RefMLP(nn.Module):                                   # networks.py:6-44 with constrain_out=True
+    def __init__(self, i, o, h):
+        super().__init__()
+        self.fc1, self.fc2, self.fc3, self.fc4 = nn.Linear(i, h), nn.Linear(h, h), nn.Linear(h, h), nn.Linear(h, o)
+
+    def forward(self, x):
+        return torch.tanh(self.fc4(F.leaky_relu(self.fc3(F.leaky_relu(self.fc2(F.leaky_relu(self.fc1(x))))))))
+
+
+@pytest.mark.parametrize("E,n_a,D,H,A", [(64, 30, 192, 180, 2), (3, 7, 188, 180, 2), (1, 1, 192, 180, 2), (5, 100, 192, 64, 3),
+                                         (2, 1024, 192, 180, 2)])
+def test_policy_matches_torch_fp32(E, n_a, D, H, A):
+    torch.manual_seed(E + n_a)
+    ref = RefMLP(D, A, H)
+    with torch.no_grad():                                   # weights large enough to leave the linear region of tanh
+        for p in ref.parameters():
+            p.mul_(3.0)
+    obs = torch.randn(E, D, n_a) * 0.7
+    obs[:, 32:, :] *= (torch.rand(E, D - 32, n_a) < 0.2)   # sparse sensed-cell rows like the env's
+    pol = DevicePolicy(D, A, H).load_state_dict(ref.state_dict())
+    act, log_pi = pol.step(obs.cuda(), explore=False)
+    with torch.no_grad():
+        want = ref(obs.permute(0, 2, 1).reshape(E * n_a, D)).reshape(E, n_a, A).permute(0, 2, 1)   # agents.py:79,95 (.t())
+    assert act.shape == (E, A, n_a)
+    torch.testing.assert_close(act.cpu(), want, rtol=1e-5, atol=2e-6)
+    assert torch.all(log_pi == 0)                           # agents.py:82: -dim * log(1)
+    # reference-shaped 2-D call (TRAIN:97-98): [obs_dim, n_a] -> [act_dim, n_a]
+    a2, lp2 = pol.step(obs[0].cuda())
+    assert a2.shape == (A, n_a) and lp2.shape == (1, n_a) and torch.equal(a2, act[0])
+    assert pol.launch_count == 2
+
+
+def test_exploration_noise_statistics_and_log_prob():
+    E, n_a, D, H, A = 2048, 30, 192, 180, 2
+    torch.manual_seed(0)
+    ref = RefMLP(D, A, H)
+    obs = torch.randn(E, D, n_a, device="cuda") * 0.3
+    pol = DevicePolicy(D, A, H, noise_scale=0.1, epsilon=0.0, seed=7).load_state_dict(ref.state_dict())
+    clean, _ = pol.step(obs)
+    noisy, log_pi = pol.step(obs, explore=True)
+    noise = (noisy - clean).double()
+    inside = (noisy.abs() < 1).all(dim=1, keepdim=True)     # columns the clamp did not touch
+    assert inside.float().mean() > 0.99
+    assert abs(float(noise.mean())) < 1e-3 and abs(float(noise.std()) - 0.1) < 1e-3
+    z = noise / 0.1
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.05         # Gaussian kurtosis
+    want_lp = -0.5 * (z ** 2).sum(dim=1, keepdim=True) - A * np.log(0.1 * np.sqrt(2 * np.pi))      # noise.py:32-37
+    sel = inside.expand_as(want_lp)
+    assert torch.allclose(log_pi.double()[sel], want_lp[sel], atol=2e-3)
+    again, _ = pol.step(obs, explore=True)
+    assert not torch.equal(again, noisy)                     # the step counter advances the stream
+    # epsilon branch (agents.py:86-88): uniform actions for the whole batch, log_pi = -dim * log 2
+    pol.epsilon = 1.0
+    uni, lp = pol.step(obs, explore=True)
+    assert float(uni.min()) >= -1 and float(uni.max()) <= 1 and abs(float(uni.mean())) < 2e-3
+    assert abs(float(uni.double().var()) - 1 / 3) < 2e-3 and torch.allclose(lp, torch.full_like(lp, -A * np.log(2.0)))

@@ -1,0 +1,25 @@
+"""Times k_policy_mlp at the BASELINE config-3 shape (65536 envs x 30 agents) with CUDA events (profiling aid)."""
+import json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from marl_llm_b200.policy import DevicePolicy
+import torch.nn as nn
+E, n_a, D, H, A = 65536, 30, 192, 180, 2
+sd = {}
+for name, (o, i) in (("fc1", (H, D)), ("fc2", (H, H)), ("fc3", (H, H)), ("fc4", (A, H))):
+    l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
+pol = DevicePolicy(D, A, H).load_state_dict(sd)
+obs = torch.randn(E, D, n_a, device="cuda")
+act = torch.empty(E, A, n_a, device="cuda")
+for _ in range(2): pol.step(obs, out=act, want_log_pi=False)
+torch.cuda.synchronize()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+K = 5
+ev[0].record()
+for _ in range(K): pol.step(obs, explore=True, out=act, want_log_pi=False)
+ev[1].record(); torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1]) / K
+flop = 2.0 * E * n_a * (D * H + H * H * 2 + H * A)
+flop_padded = 2.0 * E * n_a * (192 * 192 * 3 + 192 * A)
+print(json.dumps({"kernel": "k_policy_mlp", "agents": E * n_a, "ms": ms, "agent_forwards_per_s": E * n_a / ms * 1e3,
+                  "useful_TFLOPs": flop / ms / 1e9, "issued_TFLOPs": flop_padded / ms / 1e9}))
