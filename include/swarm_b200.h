@@ -249,6 +249,15 @@ int swarm_policy_load(swarm_policy *p, const float *w1, const float *b1, const f
  * (seed, step, column, component), not from NumPy.  log_pi: DEVICE [E][1][n_a] f32 or NULL (agents.py:82,88,91). */
 int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32_t n_a, float *act, float *log_pi, int explore,
                       float noise_scale, uint64_t seed, uint64_t step, void *stream);
+/* Arithmetic of swarm_policy_step.  SWARM_POLICY_FP32 (default): fp32 FFMA, agrees with torch's fp32 network to rounding.
+ * SWARM_POLICY_F16_TC: one persistent tcgen05 kernel (weights resident in shared memory as fp16, activations and fp32
+ * accumulators in tensor memory); ~50x faster, deviates by ~1e-3 absolute on the tanh output. */
+#define SWARM_POLICY_FP32 0
+#define SWARM_POLICY_F16_TC 1
+int swarm_policy_set_precision(swarm_policy *p, int precision);
+/* test hook: when non-NULL, the tensor-core path also writes its layer-1 accumulators (fc1 without bias) to
+ * layer1_acc_dev [E*n_a][192] f32 (device). */
+int swarm_policy_debug_buffer(swarm_policy *p, float *layer1_acc_dev);
 int64_t swarm_policy_launch_count(const swarm_policy *p);
 
 const char *swarm_last_error(void);

@@ -44,7 +44,9 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold"]
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
-POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count"]
+POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
+                  "swarm_policy_set_precision", "swarm_policy_debug_buffer"]
+SWARM_POLICY_FP32, SWARM_POLICY_F16_TC = 0, 1
 
 
 class SwarmRolloutBuffers(C.Structure):
@@ -99,6 +101,8 @@ def load():
     lib.swarm_policy_load.argtypes = [C.c_void_p] + [C.c_void_p] * 8
     lib.swarm_policy_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
                                       C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.swarm_policy_set_precision.argtypes = [C.c_void_p, C.c_int]
+    lib.swarm_policy_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.swarm_policy_launch_count.restype = C.c_int64
     lib.swarm_policy_launch_count.argtypes = [C.c_void_p]
     lib.swarm_sqrt_threshold.restype = C.c_double

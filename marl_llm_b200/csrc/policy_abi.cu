@@ -2,6 +2,8 @@
 #include "policy_kernels.cuh"
 #include "../../include/swarm_b200.h"
 
+#include <cuda_fp16.h>
+
 #include <string>
 #include <vector>
 
@@ -22,6 +24,10 @@ constexpr size_t POL_SMEM = ((size_t)2 * POL_HP * POL_M + (size_t)2 * POL_KC * P
 struct swarm_policy {
     int device, obs_dim, hidden, act_dim;
     float *d_w;          // one allocation: Wt[3][HP][HP], b[3][HP], W4[A][HP], b4[A]
+    unsigned char *d_w16; // [3][TC_W_BYTES] fp16 weights in the canonical UMMA K-major layout (tensor-core path)
+    int precision;       // SWARM_POLICY_FP32 | SWARM_POLICY_F16_TC
+    int n_sm;
+    float *debug;        // test hook: layer-1 accumulators of the tensor-core path
     bool loaded;
     int64_t launches;
 };
@@ -39,11 +45,20 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     PCU_TRY(cudaSetDevice(device));
     swarm_policy *p = new swarm_policy();
     p->device = device; p->obs_dim = obs_dim; p->hidden = hidden_dim; p->act_dim = act_dim; p->loaded = false; p->launches = 0;
+    p->precision = SWARM_POLICY_FP32; p->debug = nullptr; p->d_w16 = nullptr;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        delete p;
+        return pfail(SWARM_ERR_NO_DEVICE, "device is not sm_100 (kernels are built for sm_100a only)");
+    }
+    p->n_sm = prop.multiProcessorCount;
     const size_t n = (size_t)3 * POL_HP * POL_HP + 3 * POL_HP + (size_t)act_dim * POL_HP + act_dim;
     cudaError_t e = cudaMalloc(&p->d_w, n * sizeof(float));
     if (e != cudaSuccess) { delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
-    e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
-    if (e != cudaSuccess) { cudaFree(p->d_w); delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_w16, (size_t)3 * TC_W_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e != cudaSuccess) { cudaFree(p->d_w); cudaFree(p->d_w16); delete p; return pfail(SWARM_ERR_CUDA, std::string("policy setup: ") + cudaGetErrorString(e)); }
     *out = p;
     return SWARM_OK;
 }
@@ -52,6 +67,7 @@ int swarm_policy_destroy(swarm_policy *p) {
     if (!p) return SWARM_OK;
     cudaSetDevice(p->device);
     cudaFree(p->d_w);
+    cudaFree(p->d_w16);
     delete p;
     return SWARM_OK;
 }
@@ -77,6 +93,16 @@ int swarm_policy_load(swarm_policy *p, const float *w1, const float *b1, const f
         for (int k = 0; k < H; ++k) w4p[(size_t)j * POL_HP + k] = w4[(size_t)j * H + k];
     for (int j = 0; j < A; ++j) w4p[(size_t)A * POL_HP + j] = b4[j];
     PCU_TRY(cudaMemcpy(p->d_w, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    // tensor-core path: W[n][k] as fp16 in the canonical K-major no-swizzle UMMA layout: 8-row x 16-byte core matrices,
+    // byte address = (k/8) * TC_LBO + (n/8) * TC_SBO + (n%8) * 16 + (k%8) * 2; zero padding up to 192 x 192
+    std::vector<__half> h16((size_t)3 * POL_HP * POL_HP, __float2half(0.f));
+    for (int l = 0; l < 3; ++l)
+        for (int nn = 0; nn < H; ++nn)
+            for (int k = 0; k < Kin[l]; ++k) {
+                const size_t byte = (size_t)(k / 8) * TC_LBO + (size_t)(nn / 8) * TC_SBO + (size_t)(nn % 8) * 16 + (size_t)(k % 8) * 2;
+                h16[(size_t)l * POL_HP * POL_HP + byte / 2] = __float2half_rn(W[l][(size_t)nn * Kin[l] + k]);
+            }
+    PCU_TRY(cudaMemcpy(p->d_w16, h16.data(), (size_t)3 * TC_W_BYTES, cudaMemcpyHostToDevice));
     p->loaded = true;
     return SWARM_OK;
 }
@@ -97,10 +123,32 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
     P.W4 = p->d_w + (size_t)3 * POL_HP * POL_HP + 3 * POL_HP;
     P.b4 = P.W4 + (size_t)p->act_dim * POL_HP;
     P.slope = 0.01f; P.explore = explore; P.scale = noise_scale; P.seed = seed; P.step = step;
+    if (p->precision == SWARM_POLICY_F16_TC) {
+        PolicyTcParams Q;
+        Q.base = P; Q.w16 = p->d_w16; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
+        Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
+        const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
+        k_policy_mlp_tc<<<grid, TC_M, TC_SMEM, (cudaStream_t)stream>>>(Q);
+        PCU_TRY(cudaGetLastError());
+        p->launches++;
+        return SWARM_OK;
+    }
     const long ctas = (P.n_cols + POL_M - 1) / POL_M;
     k_policy_mlp<<<(unsigned)ctas, POL_THREADS, POL_SMEM, (cudaStream_t)stream>>>(P);
     PCU_TRY(cudaGetLastError());
     p->launches++;
+    return SWARM_OK;
+}
+
+int swarm_policy_set_precision(swarm_policy *p, int precision) {
+    if (!p || (precision != SWARM_POLICY_FP32 && precision != SWARM_POLICY_F16_TC)) return pfail(SWARM_ERR_INVALID, "bad precision");
+    p->precision = precision;
+    return SWARM_OK;
+}
+
+int swarm_policy_debug_buffer(swarm_policy *p, float *layer1_acc_dev) {
+    if (!p) return pfail(SWARM_ERR_INVALID, "null handle");
+    p->debug = layer1_acc_dev;
     return SWARM_OK;
 }
 

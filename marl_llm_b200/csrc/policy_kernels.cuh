@@ -12,6 +12,7 @@
 // and streams the (L2-resident, pre-transposed, zero-padded) weights through a double-buffered cp.async ring.
 // Each thread accumulates a 6 (outputs) x 8 (columns) register tile: 48 FFMA per 3 + 2 shared-memory vector loads.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <stdint.h>
@@ -173,6 +174,225 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy_mlp(const PolicyParam
             if (j == 0) P.log_pi[e * n_a + ag] = lp;
         }
     }
+}
+
+
+// =====================================================================================================
+// Tensor-core path: the same network as ONE persistent tcgen05 kernel (5th-generation tensor cores, accumulators and
+// the activation operand in tensor memory).
+//
+//   * one CTA per SM, 128 threads; thread t owns TMEM lane t = one agent ("column") of the current 128-agent tile;
+//   * the three 192x192 weight matrices live in shared memory for the whole kernel as fp16 in the canonical K-major
+//     no-swizzle UMMA layout (8-row x 16-byte core matrices; prepared on the host, pulled in by three bulk async copies):
+//     3 x 73 728 B — which is why this path is fp16: fp32/tf32 weights would not fit next to each other;
+//   * activations never touch shared or global memory: obs -> registers -> fp16 -> tcgen05.st -> TMEM (operand A);
+//     tcgen05.mma (M128 N192 K16, twelve per layer, issued by one thread) accumulates fp32 in TMEM; after
+//     tcgen05.commit -> mbarrier every thread pulls its row back with tcgen05.ld, adds the bias, applies leaky_relu and
+//     stores the fp16 result over operand A for the next layer;
+//   * the 180 -> 2 output layer, tanh, exploration noise and log-prob run on the fp32 registers of the last epilogue.
+// Arithmetic: fp16 operands (11-bit significands), fp32 accumulation: deviates from the fp32 network by ~1e-3 absolute on
+// the tanh output ("fast mode"; the exact path is k_policy_mlp above).
+// =====================================================================================================
+constexpr int TC_M = 128;                                   // agents per tile = TMEM lanes
+constexpr int TC_N = POL_HP;                                // 192 outputs per layer
+constexpr int TC_W_BYTES = POL_HP * POL_HP * 2;             // one layer of fp16 weights, canonical layout
+constexpr int TC_LBO = (POL_HP / 8) * 128;                  // bytes between the two 16-byte k-chunks of one MMA (next core-matrix column)
+constexpr int TC_SBO = 128;                                 // bytes between 8-row groups
+constexpr int TC_COL_D = 0, TC_COL_A = 256, TC_COLS = 512;  // TMEM columns: accumulator [0,192), operand A [256,352)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = 192, M = 128
+constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+constexpr size_t TC_SMEM = (size_t)3 * TC_W_BYTES + 3 * POL_HP * 4 + (size_t)POL_AMAX * POL_HP * 4 + POL_AMAX * 4 + 64;
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, SWIZZLE_NONE, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((TC_LBO >> 4) & 0x3fff) << 16) | ((uint64_t)((TC_SBO >> 4) & 0x3fff) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);            // .x = lo -> bits [0,16): the lower k index sits in the lower half
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+#define TC_LD32(taddr, v)                                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),   \
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),      \
+                   "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),     \
+                   "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                                       \
+                 : "r"(taddr) : "memory")
+#define TC_ST16(taddr, v)                                                                                              \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                   \
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), \
+                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory")
+
+struct PolicyTcParams {
+    PolicyParams base;                 // obs / act / log_pi / sizes / exploration (weight pointers unused)
+    const unsigned char *w16;          // [3][TC_W_BYTES] fp16 weights in canonical UMMA layout (device)
+    const float *small;                // b[3][192], W4[A][192], b4[A] fp32 (device)
+    float *debug;                      // optional [n_cols][192] fp32: layer-1 pre-activations (tests), or NULL
+    long n_tiles;
+};
+
+__global__ void __launch_bounds__(TC_M, 1) k_policy_mlp_tc(const PolicyTcParams Q) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    unsigned char *sW = tsm;                                             // 3 layers of weights
+    float *sB = reinterpret_cast<float *>(sW + 3 * TC_W_BYTES);          // [3][192]
+    float *sW4 = sB + 3 * POL_HP;                                        // [AMAX][192]
+    float *sb4 = sW4 + POL_AMAX * POL_HP;                                // [AMAX]
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(sb4 + POL_AMAX);      // weights landed
+    uint64_t *bar_mma = bar_w + 1;                                       // a layer's MMAs retired
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    const PolicyParams &P = Q.base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int A = P.A, n_a = P.n_a;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(bar_w)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(bar_mma)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar_w)), "r"(3u * TC_W_BYTES) : "memory");
+        for (int l = 0; l < 3; ++l)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(s_u32(sW + l * TC_W_BYTES)), "l"(Q.w16 + (size_t)l * TC_W_BYTES), "r"((uint32_t)TC_W_BYTES), "r"(s_u32(bar_w)) : "memory");
+    }
+    for (int k = tid; k < 3 * POL_HP + A * POL_HP + A; k += TC_M) {      // biases + output layer: sB, sW4 (A rows), sb4
+        const float v = Q.small[k];
+        if (k < 3 * POL_HP) sB[k] = v;
+        else if (k < 3 * POL_HP + A * POL_HP) sW4[k - 3 * POL_HP] = v;
+        else sb4[k - 3 * POL_HP - A * POL_HP] = v;
+    }
+    if (warp == 0) {                                                     // one warp allocates the tensor memory of this SM
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"((uint32_t)TC_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);    // this warp's 32-lane quadrant
+    uint32_t par_mma = 0;
+    bool weights_ready = false;
+
+#pragma unroll 1
+    for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x) {
+        const long col = tile * TC_M + tid;
+        const bool valid = col < P.n_cols;
+        const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
+        // ---- observation row -> fp16 -> operand A in TMEM (6 stores of 16 columns = 32 features each)
+        const float *orow = P.obs + e * (long)P.K0 * n_a + ag;
+#pragma unroll 1
+        for (int c = 0; c < POL_HP / 32; ++c) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int k = c * 32 + 2 * q;
+                const float v0 = (valid && k < P.K0) ? orow[(long)k * n_a] : 0.f;
+                const float v1 = (valid && k + 1 < P.K0) ? orow[(long)(k + 1) * n_a] : 0.f;
+                r[q] = pack_h2(v0, v1);
+            }
+            TC_ST16(lane_base + TC_COL_A + c * 16, r);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        float out[POL_AMAX];
+#pragma unroll
+        for (int j = 0; j < POL_AMAX; ++j) out[j] = 0.f;
+
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();                                             // operand A complete, accumulator drained
+            if (tid == 0) {
+                if (!weights_ready) tc_mbar_wait(bar_w, 0);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t wbase = s_u32(sW + layer * TC_W_BYTES);
+#pragma unroll 1
+                for (int j = 0; j < POL_HP / 16; ++j) {                  // K = 16 per instruction: two 16-byte k-chunks
+                    const uint64_t bdesc = tc_smem_desc(wbase + (uint32_t)j * 2u * TC_LBO);
+                    const uint32_t acc = j > 0 ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                        ::"r"(tmem + TC_COL_D), "r"(tmem + TC_COL_A + j * 8), "l"(bdesc), "r"(TC_IDESC), "r"(acc), "r"(0u) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar_mma)) : "memory");
+            }
+            weights_ready = true;
+            tc_mbar_wait(bar_mma, par_mma); par_mma ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float *bias = sB + layer * POL_HP;
+#pragma unroll 1
+            for (int c = 0; c < POL_HP / 32; ++c) {                      // 32 accumulator columns at a time
+                uint32_t v[32];
+                TC_LD32(lane_base + TC_COL_D + c * 32, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (Q.debug && layer == 0 && valid) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) Q.debug[col * POL_HP + c * 32 + q] = __uint_as_float(v[q]);
+                }
+                float h[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const float s = __uint_as_float(v[q]) + bias[c * 32 + q];
+                    h[q] = s > 0.f ? s : s * P.slope;
+                }
+                if (layer < 2) {
+                    uint32_t r[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) r[q] = pack_h2(h[2 * q], h[2 * q + 1]);
+                    TC_ST16(lane_base + TC_COL_A + c * 16, r);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < POL_AMAX; ++j) {
+                        if (j < A) {
+                            float s = out[j];
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) s = fmaf(h[q], sW4[j * POL_HP + c * 32 + q], s);
+                            out[j] = s;
+                        }
+                    }
+                }
+            }
+            if (layer < 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        // ---- tanh, exploration, outputs (same definitions as k_policy_mlp)
+        if (valid) {
+            float q2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < POL_AMAX; ++j) {
+                if (j >= A) break;
+                float a = tanhf(out[j] + sb4[j]);
+                if (P.explore == 1) {
+                    const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                    const float u1 = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);
+                    const float u2 = (float)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
+                    const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+                    q2 += g * g;
+                    a = fminf(fmaxf(a + g * P.scale, -1.f), 1.f);
+                } else if (P.explore == 2) {
+                    const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                    a = (float)(r >> 40) * (2.0f / 16777216.0f) - 1.0f;
+                }
+                P.act[(e * A + j) * n_a + ag] = a;
+            }
+            if (P.log_pi) {
+                float lp = 0.f;
+                if (P.explore == 2) lp = -(float)A * 0.69314718056f;
+                else if (P.explore == 1) lp = -0.5f * q2 - (float)A * logf(P.scale * 2.50662827463f);
+                P.log_pi[e * n_a + ag] = lp;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_COLS) : "memory");
 }
 
 }  // namespace swarm

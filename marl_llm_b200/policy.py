@@ -18,7 +18,7 @@ from ._lib import SwarmError, check
 
 
 class DevicePolicy:
-    def __init__(self, obs_dim, act_dim, hidden_dim=180, device=0, noise_scale=0.1, epsilon=0.0, seed=0):
+    def __init__(self, obs_dim, act_dim, hidden_dim=180, device=0, noise_scale=0.1, epsilon=0.0, seed=0, precision="fp32"):
         if not torch.cuda.is_available():
             raise SwarmError("DevicePolicy needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -30,6 +30,14 @@ class DevicePolicy:
         check(self.lib.swarm_policy_create(self.device.index, self.obs_dim, self.hidden_dim, self.act_dim, C.byref(h)),
               "swarm_policy_create")
         self._h = h
+        self.set_precision(precision)
+
+    def set_precision(self, precision):
+        """'fp32': exact path (FFMA, agrees with torch fp32 to rounding).  'f16_tc': persistent tcgen05 kernel, fp16 operands
+        with fp32 accumulation in tensor memory (fast mode, ~1e-3 absolute deviation on the tanh output)."""
+        mode = {"fp32": _lib.SWARM_POLICY_FP32, "f16_tc": _lib.SWARM_POLICY_F16_TC}[precision]
+        check(self.lib.swarm_policy_set_precision(self._h, mode), "swarm_policy_set_precision")
+        self.precision = precision
 
     def close(self):
         if getattr(self, "_h", None):

@@ -69,3 +69,44 @@ def test_exploration_noise_statistics_and_log_prob():
     uni, lp = pol.step(obs, explore=True)
     assert float(uni.min()) >= -1 and float(uni.max()) <= 1 and abs(float(uni.mean())) < 2e-3
     assert abs(float(uni.double().var()) - 1 / 3) < 2e-3 and torch.allclose(lp, torch.full_like(lp, -A * np.log(2.0)))
+
+
+def _f16_pipeline(ref, x):
+    """torch emulation of the tensor-core path: fp16 operands, fp32 accumulation, fp16 re-rounding of h1/h2, fp32 tail."""
+    r = lambda t: t.half().float()     # noqa: E731
+    h = x
+    for k, fc in enumerate((ref.fc1, ref.fc2, ref.fc3)):
+        h = F.leaky_relu(r(h).double() @ r(fc.weight).double().t() + fc.bias.double()).float()
+    return torch.tanh(h.double() @ ref.fc4.weight.double().t() + ref.fc4.bias.double()).float()
+
+
+@pytest.mark.parametrize("E,n_a", [(64, 30), (5, 7), (1, 1), (3, 1024), (300, 30)])
+def test_tensor_core_policy_layer1_and_outputs(E, n_a):
+    """tcgen05 path: (1) its raw layer-1 accumulators equal fc1 on fp16-rounded operands (fp32 accumulation: 1e-4),
+    which pins the UMMA descriptors / TMEM operand layout; (2) the actions equal a torch emulation of the fp16 pipeline
+    to 5e-4 and the fp32 network to 5e-3 (documented fast-mode deviation)."""
+    D, H, A = 192, 180, 2
+    torch.manual_seed(11 + n_a)
+    ref = RefMLP(D, A, H)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.mul_(2.0)
+    obs = torch.randn(E, D, n_a) * 0.7
+    pol = DevicePolicy(D, A, H, precision="f16_tc").load_state_dict(ref.state_dict())
+    dbg = torch.full((E * n_a, 192), float("nan"), device="cuda")
+    pol.lib.swarm_policy_debug_buffer(pol._h, dbg.data_ptr())
+    act, _ = pol.step(obs.cuda())
+    pol.lib.swarm_policy_debug_buffer(pol._h, None)
+    x = obs.permute(0, 2, 1).reshape(E * n_a, D)
+    with torch.no_grad():
+        want1 = (x.half().double() @ ref.fc1.weight.half().double().t()).float()
+        torch.testing.assert_close(dbg.cpu()[:, :H], want1, rtol=1e-4, atol=1e-4)
+        assert torch.all(dbg[:, H:] == 0)                       # zero-padded outputs
+        emu = _f16_pipeline(ref, x).reshape(E, n_a, A).permute(0, 2, 1)
+        exact = ref(x).reshape(E, n_a, A).permute(0, 2, 1)
+    torch.testing.assert_close(act.cpu(), emu, rtol=0, atol=5e-4)   # fp16 re-rounding of h1/h2 can flip at ties
+    torch.testing.assert_close(act.cpu(), exact, rtol=0, atol=5e-3)
+    # same handle, exact path again
+    pol.set_precision("fp32")
+    act32, _ = pol.step(obs.cuda())
+    torch.testing.assert_close(act32.cpu(), exact, rtol=1e-5, atol=2e-6)

@@ -8,7 +8,8 @@ E, n_a, D, H, A = 65536, 30, 192, 180, 2
 sd = {}
 for name, (o, i) in (("fc1", (H, D)), ("fc2", (H, H)), ("fc3", (H, H)), ("fc4", (A, H))):
     l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
-pol = DevicePolicy(D, A, H).load_state_dict(sd)
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+pol = DevicePolicy(D, A, H, precision=prec).load_state_dict(sd)
 obs = torch.randn(E, D, n_a, device="cuda")
 act = torch.empty(E, A, n_a, device="cuda")
 for _ in range(2): pol.step(obs, out=act, want_log_pi=False)
@@ -21,5 +22,5 @@ ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1]) / K
 flop = 2.0 * E * n_a * (D * H + H * H * 2 + H * A)
 flop_padded = 2.0 * E * n_a * (192 * 192 * 3 + 192 * A)
-print(json.dumps({"kernel": "k_policy_mlp", "agents": E * n_a, "ms": ms, "agent_forwards_per_s": E * n_a / ms * 1e3,
+print(json.dumps({"kernel": "k_policy_mlp" + ("_tc" if prec == "f16_tc" else ""), "agents": E * n_a, "ms": ms, "agent_forwards_per_s": E * n_a / ms * 1e3,
                   "useful_TFLOPs": flop / ms / 1e9, "issued_TFLOPs": flop_padded / ms / 1e9}))
