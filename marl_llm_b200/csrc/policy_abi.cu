@@ -128,7 +128,7 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
         Q.base = P; Q.w16 = p->d_w16; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
         Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
         const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
-        k_policy_mlp_tc<<<grid, TC_M, TC_SMEM, (cudaStream_t)stream>>>(Q);
+        k_policy_mlp_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(Q);
         PCU_TRY(cudaGetLastError());
         p->launches++;
         return SWARM_OK;

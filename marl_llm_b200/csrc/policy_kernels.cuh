@@ -181,7 +181,8 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy_mlp(const PolicyParam
 // Tensor-core path: the same network as ONE persistent tcgen05 kernel (5th-generation tensor cores, accumulators and
 // the activation operand in tensor memory).
 //
-//   * one CTA per SM, 128 threads; thread t owns TMEM lane t = one agent ("column") of the current 128-agent tile;
+//   * one CTA per SM; warps 0-3 ("compute"): thread t owns TMEM lane t = one agent ("column") of the current 128-agent
+//     tile; warps 4-7 ("loader") convert the NEXT tile's observations into the second operand-A buffer meanwhile;
 //   * the three 192x192 weight matrices live in shared memory for the whole kernel as fp16 in the canonical K-major
 //     no-swizzle UMMA layout (8-row x 16-byte core matrices; prepared on the host, pulled in by three bulk async copies):
 //     3 x 73 728 B — which is why this path is fp16: fp32/tf32 weights would not fit next to each other;
@@ -201,7 +202,7 @@ constexpr int TC_SBO = 128;                                 // bytes between 8-r
 constexpr int TC_COL_D = 0, TC_COL_A = 256, TC_COLS = 512;  // TMEM columns: accumulator [0,192), operand A [256,352)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = 192, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-constexpr size_t TC_SMEM = (size_t)3 * TC_W_BYTES + 3 * POL_HP * 4 + (size_t)POL_AMAX * POL_HP * 4 + POL_AMAX * 4 + 64;
+constexpr size_t TC_SMEM = (size_t)3 * TC_W_BYTES + 3 * POL_HP * 4 + (size_t)POL_AMAX * POL_HP * 4 + POL_AMAX * 4 + 96;
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -241,7 +242,21 @@ struct PolicyTcParams {
     long n_tiles;
 };
 
-__global__ void __launch_bounds__(TC_M, 1) k_policy_mlp_tc(const PolicyTcParams Q) {
+constexpr int TC_LOADERS = 2;               // loader warps per TMEM lane quadrant (each converts 192 / TC_LOADERS features of a row)
+constexpr int TC_THREADS = (1 + TC_LOADERS) * TC_M;   // warps 0-3: MMA issue + epilogues ("compute");  warps 4..: observation loaders
+constexpr int TC_COL_A1 = TC_COL_A + POL_HP / 2;   // second operand-A buffer (the loader fills one while the other is in use)
+
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {      // arrives on bar once every tcgen05.mma issued so far has retired
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcParams Q) {
     extern __shared__ __align__(128) unsigned char tsm[];
     unsigned char *sW = tsm;                                             // 3 layers of weights
     float *sB = reinterpret_cast<float *>(sW + 3 * TC_W_BYTES);          // [3][192]
@@ -249,21 +264,24 @@ __global__ void __launch_bounds__(TC_M, 1) k_policy_mlp_tc(const PolicyTcParams 
     float *sb4 = sW4 + POL_AMAX * POL_HP;                                // [AMAX]
     uint64_t *bar_w = reinterpret_cast<uint64_t *>(sb4 + POL_AMAX);      // weights landed
     uint64_t *bar_mma = bar_w + 1;                                       // a layer's MMAs retired
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    uint64_t *bar_full = bar_mma + 1;                                    // [2] loader -> compute: operand-A buffer b holds a tile's observations
+    uint64_t *bar_free = bar_full + 2;                                   // [2] compute -> loader: the last MMA reading buffer b has retired
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_free + 2);
     const PolicyParams &P = Q.base;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int A = P.A, n_a = P.n_a;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(bar_w)) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(bar_mma)) : "memory");
+        tc_mbar_init(bar_w, 1); tc_mbar_init(bar_mma, 1);
+        tc_mbar_init(&bar_full[0], TC_LOADERS * TC_M); tc_mbar_init(&bar_full[1], TC_LOADERS * TC_M);
+        tc_mbar_init(&bar_free[0], 1); tc_mbar_init(&bar_free[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar_w)), "r"(3u * TC_W_BYTES) : "memory");
         for (int l = 0; l < 3; ++l)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(s_u32(sW + l * TC_W_BYTES)), "l"(Q.w16 + (size_t)l * TC_W_BYTES), "r"((uint32_t)TC_W_BYTES), "r"(s_u32(bar_w)) : "memory");
     }
-    for (int k = tid; k < 3 * POL_HP + A * POL_HP + A; k += TC_M) {      // biases + output layer: sB, sW4 (A rows), sb4
+    for (int k = tid; k < 3 * POL_HP + A * POL_HP + A; k += TC_THREADS) { // biases + output layer: sB, sW4 (A rows), sb4
         const float v = Q.small[k];
         if (k < 3 * POL_HP) sB[k] = v;
         else if (k < 3 * POL_HP + A * POL_HP) sW4[k - 3 * POL_HP] = v;
@@ -277,116 +295,167 @@ __global__ void __launch_bounds__(TC_M, 1) k_policy_mlp_tc(const PolicyTcParams 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);    // this warp's 32-lane quadrant
-    uint32_t par_mma = 0;
-    bool weights_ready = false;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches the TMEM lane quadrant warp % 4
+    const int row = tid & (TC_M - 1);                                    // TMEM lane = agent of the tile
 
+    if (warp >= 4) {
+        // ================= loader: observation row -> fp16 -> operand-A buffer (it & 1), one tile ahead of the MMAs
+        int it = 0;
 #pragma unroll 1
-    for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x) {
-        const long col = tile * TC_M + tid;
-        const bool valid = col < P.n_cols;
-        const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
-        // ---- observation row -> fp16 -> operand A in TMEM (6 stores of 16 columns = 32 features each)
-        const float *orow = P.obs + e * (long)P.K0 * n_a + ag;
-#pragma unroll 1
-        for (int c = 0; c < POL_HP / 32; ++c) {
-            uint32_t r[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int k = c * 32 + 2 * q;
-                const float v0 = (valid && k < P.K0) ? orow[(long)k * n_a] : 0.f;
-                const float v1 = (valid && k + 1 < P.K0) ? orow[(long)(k + 1) * n_a] : 0.f;
-                r[q] = pack_h2(v0, v1);
-            }
-            TC_ST16(lane_base + TC_COL_A + c * 16, r);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        float out[POL_AMAX];
-#pragma unroll
-        for (int j = 0; j < POL_AMAX; ++j) out[j] = 0.f;
-
-#pragma unroll 1
-        for (int layer = 0; layer < 3; ++layer) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();                                             // operand A complete, accumulator drained
-            if (tid == 0) {
-                if (!weights_ready) tc_mbar_wait(bar_w, 0);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t wbase = s_u32(sW + layer * TC_W_BYTES);
-#pragma unroll 1
-                for (int j = 0; j < POL_HP / 16; ++j) {                  // K = 16 per instruction: two 16-byte k-chunks
-                    const uint64_t bdesc = tc_smem_desc(wbase + (uint32_t)j * 2u * TC_LBO);
-                    const uint32_t acc = j > 0 ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                        ::"r"(tmem + TC_COL_D), "r"(tmem + TC_COL_A + j * 8), "l"(bdesc), "r"(TC_IDESC), "r"(acc), "r"(0u) : "memory");
+        for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            if (tid == TC_M) {  // pull the NEXT tile's observations (a contiguous run of whole envs) into the L2 while this one is converted
+                const long nt = tile + gridDim.x;
+                if (nt < Q.n_tiles) {
+                    const long e0 = nt * TC_M / n_a;
+                    long e1 = (nt * TC_M + TC_M - 1) / n_a; if (e1 * n_a >= P.n_cols) e1 = (P.n_cols - 1) / n_a;
+                    const size_t env_bytes = (size_t)P.K0 * n_a * sizeof(float);
+                    if ((env_bytes & 15) == 0)
+                        for (long ee = e0; ee <= e1; ++ee)
+                            for (size_t off = 0; off < env_bytes; off += 32768) {
+                                const uint32_t sz = (uint32_t)(env_bytes - off < 32768 ? env_bytes - off : 32768);
+                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(P.obs) + ee * env_bytes + off), "r"(sz) : "memory");
+                            }
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar_mma)) : "memory");
             }
-            weights_ready = true;
-            tc_mbar_wait(bar_mma, par_mma); par_mma ^= 1u;
+            if (it >= 2) tc_mbar_wait(&bar_free[b], (uint32_t)((it >> 1) - 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const float *bias = sB + layer * POL_HP;
-#pragma unroll 1
-            for (int c = 0; c < POL_HP / 32; ++c) {                      // 32 accumulator columns at a time
-                uint32_t v[32];
-                TC_LD32(lane_base + TC_COL_D + c * 32, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (Q.debug && layer == 0 && valid) {
+            const long col = tile * TC_M + row;
+            const bool valid = col < P.n_cols;
+            const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
+            const float *orow = P.obs + e * (long)P.K0 * n_a + ag;
+            const uint32_t abase = lane_base + (b ? TC_COL_A1 : TC_COL_A);
+            constexpr int FPL = POL_HP / TC_LOADERS;                     // features per loader thread
+            const int k_lo = ((warp - 4) >> 2) * FPL;
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) Q.debug[col * POL_HP + c * 32 + q] = __uint_as_float(v[q]);
-                }
-                float h[32];
+            for (int c = 0; c < FPL / 32; ++c) {                         // fully unrolled: all FPL loads of the row are in flight together
+                float f[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
-                    const float s = __uint_as_float(v[q]) + bias[c * 32 + q];
-                    h[q] = s > 0.f ? s : s * P.slope;
+                    const int k = k_lo + c * 32 + q;
+                    f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                 }
-                if (layer < 2) {
-                    uint32_t r[16];
+                uint32_t r[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) r[q] = pack_h2(h[2 * q], h[2 * q + 1]);
-                    TC_ST16(lane_base + TC_COL_A + c * 16, r);
-                } else {
+                for (int q = 0; q < 16; ++q) r[q] = pack_h2(f[2 * q], f[2 * q + 1]);
+                TC_ST16(abase + (k_lo >> 1) + c * 16, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(&bar_full[b]);
+        }
+    } else {
+        // ================= compute: thread 0 issues the MMAs, all four warps run the epilogues
+        uint32_t par_mma = 0;
+        int it = 0;
+#pragma unroll 1
+        for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t acol = b ? TC_COL_A1 : TC_COL_A;
+            const long col = tile * TC_M + row;
+            const bool valid = col < P.n_cols;
+            const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
+            float out[POL_AMAX];
 #pragma unroll
-                    for (int j = 0; j < POL_AMAX; ++j) {
-                        if (j < A) {
-                            float s = out[j];
+            for (int j = 0; j < POL_AMAX; ++j) out[j] = 0.f;
+#pragma unroll 1
+            for (int layer = 0; layer < 3; ++layer) {
+                if (layer > 0) {                                         // operand A rewritten by every epilogue thread
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                if (tid == 0) {
+                    if (it == 0 && layer == 0) tc_mbar_wait(bar_w, 0);
+                    if (layer == 0) tc_mbar_wait(&bar_full[b], (uint32_t)(it >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t wbase = s_u32(sW + layer * TC_W_BYTES);
+#pragma unroll 1
+                    for (int j = 0; j < POL_HP / 16; ++j) {              // K = 16 per instruction: two 16-byte k-chunks
+                        const uint64_t bdesc = tc_smem_desc(wbase + (uint32_t)j * 2u * TC_LBO);
+                        const uint32_t acc = j > 0 ? 1u : 0u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                            ::"r"(tmem + TC_COL_D), "r"(tmem + acol + j * 8), "l"(bdesc), "r"(TC_IDESC), "r"(acc), "r"(0u) : "memory");
+                    }
+                    tc_commit(bar_mma);
+                    if (layer == 2) tc_commit(&bar_free[b]);             // buffer b may be refilled once these MMAs have retired
+                }
+                tc_mbar_wait(bar_mma, par_mma); par_mma ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float *bias = sB + layer * POL_HP;
+#pragma unroll 1
+                for (int c = 0; c < POL_HP / 32; ++c) {                  // 32 accumulator columns at a time
+                    uint32_t v[32];
+                    TC_LD32(lane_base + TC_COL_D + c * 32, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (Q.debug && layer == 0 && valid) {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q) s = fmaf(h[q], sW4[j * POL_HP + c * 32 + q], s);
-                            out[j] = s;
+                        for (int q = 0; q < 32; ++q) Q.debug[col * POL_HP + c * 32 + q] = __uint_as_float(v[q]);
+                    }
+                    float h[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 b4v = *reinterpret_cast<const float4 *>(bias + c * 32 + q4 * 4);
+                        const float bb[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float s_ = __uint_as_float(v[q4 * 4 + u]) + bb[u];
+                            h[q4 * 4 + u] = s_ > 0.f ? s_ : s_ * P.slope;
+                        }
+                    }
+                    if (layer < 2) {
+                        uint32_t r[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) r[q] = pack_h2(h[2 * q], h[2 * q + 1]);
+                        TC_ST16(lane_base + acol + c * 16, r);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < POL_AMAX; ++j) {
+                            if (j < A) {
+                                float s_ = out[j];
+#pragma unroll
+                                for (int q4 = 0; q4 < 8; ++q4) {
+                                    const float4 w = *reinterpret_cast<const float4 *>(sW4 + j * POL_HP + c * 32 + q4 * 4);
+                                    s_ = fmaf(h[q4 * 4], w.x, s_); s_ = fmaf(h[q4 * 4 + 1], w.y, s_);
+                                    s_ = fmaf(h[q4 * 4 + 2], w.z, s_); s_ = fmaf(h[q4 * 4 + 3], w.w, s_);
+                                }
+                                out[j] = s_;
+                            }
                         }
                     }
                 }
+                if (layer < 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
-            if (layer < 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        }
-        // ---- tanh, exploration, outputs (same definitions as k_policy_mlp)
-        if (valid) {
-            float q2 = 0.f;
+            // every compute thread has read its accumulator row before thread 0 may start the next tile's first MMA
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---- tanh, exploration, outputs (same definitions as k_policy_mlp)
+            if (valid) {
+                float q2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < POL_AMAX; ++j) {
-                if (j >= A) break;
-                float a = tanhf(out[j] + sb4[j]);
-                if (P.explore == 1) {
-                    const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
-                    const float u1 = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);
-                    const float u2 = (float)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
-                    const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-                    q2 += g * g;
-                    a = fminf(fmaxf(a + g * P.scale, -1.f), 1.f);
-                } else if (P.explore == 2) {
-                    const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
-                    a = (float)(r >> 40) * (2.0f / 16777216.0f) - 1.0f;
+                for (int j = 0; j < POL_AMAX; ++j) {
+                    if (j >= A) break;
+                    float a = tanhf(out[j] + sb4[j]);
+                    if (P.explore == 1) {
+                        const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                        const float u1 = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);
+                        const float u2 = (float)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
+                        const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+                        q2 += g * g;
+                        a = fminf(fmaxf(a + g * P.scale, -1.f), 1.f);
+                    } else if (P.explore == 2) {
+                        const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                        a = (float)(r >> 40) * (2.0f / 16777216.0f) - 1.0f;
+                    }
+                    P.act[(e * A + j) * n_a + ag] = a;
                 }
-                P.act[(e * A + j) * n_a + ag] = a;
-            }
-            if (P.log_pi) {
-                float lp = 0.f;
-                if (P.explore == 2) lp = -(float)A * 0.69314718056f;
-                else if (P.explore == 1) lp = -0.5f * q2 - (float)A * logf(P.scale * 2.50662827463f);
-                P.log_pi[e * n_a + ag] = lp;
+                if (P.log_pi) {
+                    float lp = 0.f;
+                    if (P.explore == 2) lp = -(float)A * 0.69314718056f;
+                    else if (P.explore == 1) lp = -0.5f * q2 - (float)A * logf(P.scale * 2.50662827463f);
+                    P.log_pi[e * n_a + ag] = lp;
+                }
             }
         }
     }
