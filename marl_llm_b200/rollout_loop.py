@@ -1,0 +1,29 @@
+"""The rollout phase of the reference's training loop (marl_llm/train/train_assembly.py:91-111) with every stage on the
+device: policy (DevicePolicy) -> env.step (BatchedAssemblySim) -> buffer.push (ReplayBufferAgent).  Nothing crosses PCIe
+inside the loop; per-step statistics stay on the device until the caller asks for them.
+
+    for et in range(episode_length):                       TRAIN:91
+        actions = maddpg.step(obs, explore=True)           TRAIN:97-99   -> policy.step(obs_prev, explore)
+        next_obs, rew, done, _, prior = env.step(actions)  TRAIN:102     -> sim.step(actions)
+        buffer.push(obs, actions, rew, next_obs, done, index, prior)     TRAIN:105-106
+        obs = next_obs                                      TRAIN:107
+
+The simulator owns ONE observation buffer, so the loop keeps the previous observation in a second tensor (a device copy
+per step; the push kernel reads both)."""
+import torch
+
+
+def rollout(sim, policy, buffer, steps, explore=True, index=None):
+    """Runs `steps` environment steps from the simulator's current observation.  Returns the per-step mean reward
+    ([steps] float64 CUDA tensor; TRAIN:110 accumulates np.mean(rewards) per step)."""
+    index = index if index is not None else slice(0, sim.n_a)
+    obs_prev = sim.obs.clone()
+    act = torch.empty(sim.E, policy.act_dim, sim.n_a, dtype=torch.float32, device=sim.device)
+    mean_rew = torch.zeros(steps, dtype=torch.float64, device=sim.device)
+    for t in range(steps):
+        _, log_pi = policy.step(obs_prev, explore=explore, out=act)
+        next_obs, rew, done, _, prior = sim.step(act)
+        buffer.push(obs_prev, act, rew, next_obs, done, index, prior, log_pi)
+        mean_rew[t] = rew.double().mean()
+        obs_prev.copy_(next_obs)
+    return mean_rew

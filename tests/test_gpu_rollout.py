@@ -78,3 +78,35 @@ def test_agent_slice_and_errors():
     assert_same(dev, orc)
     with pytest.raises(IndexError):
         dev.gather([dev.total_length])
+
+
+def test_device_rollout_loop_fills_the_buffer_consistently():
+    """policy -> step -> push entirely on the device (marl_llm_b200/rollout_loop.py, TRAIN:91-111): the rows pushed at
+    step t are the transposes of what the simulator / policy held at that step, and next_obs of step t is obs of t+1."""
+    import torch.nn as nn
+    from marl_llm_b200.batched import BatchedAssemblySim, r_avoid_for
+    from marl_llm_b200.policy import DevicePolicy
+    from marl_llm_b200.rollout_loop import rollout
+    from tests.helpers import load_shapes
+    shapes = load_shapes()
+    E, n_a, T = 16, 30, 6
+    sim = BatchedAssemblySim(E, n_a, int(shapes["n_g"].max()), r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"]))
+    sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+    sim.reset(seed=3)
+    torch.manual_seed(0)
+    sd = {}
+    for name, (o, i) in (("fc1", (180, 192)), ("fc2", (180, 180)), ("fc3", (180, 180)), ("fc4", (2, 180))):
+        l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
+    pol = DevicePolicy(192, 2, 180, noise_scale=0.3, seed=5).load_state_dict(sd)
+    buf = ReplayBufferAgent(T, E * n_a, slice(0, n_a), 192, 2)
+    obs0 = sim.obs.clone()
+    mean_rew = rollout(sim, pol, buf, T)
+    n = E * n_a
+    assert len(buf) == T * n and buf.curr_i == 0 and mean_rew.shape == (T,)
+    rows = lambda t: t.permute(0, 2, 1).reshape(n, -1)     # noqa: E731
+    assert torch.equal(buf.obs_buffs[:n], rows(obs0))
+    for t in range(T - 1):
+        assert torch.equal(buf.next_obs_buffs[t * n:(t + 1) * n], buf.obs_buffs[(t + 1) * n:(t + 2) * n]), t
+    assert torch.equal(buf.next_obs_buffs[(T - 1) * n:], rows(sim.obs))
+    assert torch.equal(buf.rew_buffs[(T - 1) * n:], rows(sim.reward)) and torch.equal(buf.ac_prior_buffs[(T - 1) * n:], rows(sim.a_prior))
+    assert float(buf.ac_buffs.abs().max()) <= 1.0 and float(buf.log_pi_buffs.abs().sum()) > 0
