@@ -182,6 +182,57 @@ def port_rollouts(orc, shapes, n_a, threads, envs, steps):
     return dict(value=envs * steps * n_a / dt, envs=envs, seconds=dt)
 
 
+def widened_path_numbers(torch, sim, act, hbm_peak):
+    """Device-timed numbers of the rows built next to the step path: k_rollout_push against the HBM roofline,
+    the policy MLP (fp32 exact path and tcgen05 fp16 path), and the rollout loop policy -> step -> push with nothing on the host."""
+    import torch.nn as nn
+    from marl_llm_b200.policy import DevicePolicy
+    from marl_llm_b200.rollout import ReplayBufferAgent
+    E, n_a, D, A, H = sim.E, sim.n_a, sim.obs_dim, 2, 180
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / k
+
+    torch.manual_seed(0)
+    sd = {}
+    for name, (o, i) in (("fc1", (H, D)), ("fc2", (H, H)), ("fc3", (H, H)), ("fc4", (A, H))):
+        lin = nn.Linear(i, o); sd[name + ".weight"] = lin.weight; sd[name + ".bias"] = lin.bias
+    pol = DevicePolicy(D, A, H, noise_scale=0.5).load_state_dict(sd)
+    buf = ReplayBufferAgent(4, E * n_a, slice(0, n_a), D, A)
+    obs_prev, act2 = sim.obs.clone(), torch.empty_like(act)
+    idx = slice(0, n_a)
+    rows = E * n_a
+    push_ms = timed(lambda: buf.push(obs_prev, act, sim.reward, sim.obs, sim.done, idx, sim.a_prior), 10)
+    push_bytes = rows * (2 * D * 4 * 2 + 2 * A * 4 * 2 + 4 * 2 + 1 + 4)
+    pol_fp32_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 3)
+    pol.set_precision("f16_tc")
+    pol_tc_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 20)
+
+    def loop_step():
+        _, lp = pol.step(obs_prev, explore=True, out=act2)
+        nxt, rew, done, _, prior = sim.step(act2)
+        buf.push(obs_prev, act2, rew, nxt, done, idx, prior, lp)
+        obs_prev.copy_(nxt)
+    loop_ms = timed(loop_step, 20)
+    flop = 2.0 * rows * (D * H + 2 * H * H + H * A)
+    return {
+        "rollout_push": {"kernel": "swarm::k_rollout_push_tma", "ms": push_ms, "GBps": push_bytes / push_ms / 1e6,
+                         "frac_of_hbm_peak": push_bytes / push_ms / 1e6 / hbm_peak, "rows": rows},
+        "policy_fp32": {"kernel": "swarm::k_policy_mlp", "ms": pol_fp32_ms, "TFLOPs": flop / pol_fp32_ms / 1e9},
+        "policy_f16_tc": {"kernel": "swarm::k_policy_mlp_tc (tcgen05, TMEM)", "ms": pol_tc_ms, "TFLOPs": flop / pol_tc_ms / 1e9},
+        "device_rollout_loop": {"stages": "policy(f16_tc) -> step -> push -> obs copy", "ms_per_step": loop_ms,
+                                "agent_steps_per_s": rows / loop_ms * 1e3},
+    }
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -197,6 +248,7 @@ def main():
     ap.add_argument("--brute-force-scan", action="store_true", help="A/B: disable the word-box culling of the grid scan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rollout-storage / policy / device-loop measurements")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-steps", type=int, default=200)
     ap.add_argument("--ref-envs", type=int, default=256)
@@ -273,7 +325,9 @@ def main():
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "swarm::k_step", "launch_ms": launch_ms,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": ("swarm::k_step<PH=1> + swarm::k_step<PH=2> (one step = two launches; the second is the dominant one)"
+                           if launches == 2 * K else "swarm::k_step"), "launch_ms": launch_ms,
                 "algorithmic_bytes_per_agent_step": bytes_per_agent}
     prof = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.isfile(prof):
@@ -323,6 +377,11 @@ def main():
             cpu = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{r['envs']} envs x 50 steps, oracle C port, {cores} OpenMP threads"}
 
+    # ---- widened path: replay push, on-device policy, whole device-resident rollout loop (rank 0, N=1) ----
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras and not parity and n_a == 30:
+        extras = widened_path_numbers(torch, sim, acts[0], peak)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -337,6 +396,7 @@ def main():
                        "actions": f"ring of {ring} pre-generated device buffers"},
             "last_step_stats": {"mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "widened_path": extras,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -60,14 +60,19 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
 
 typedef void (*step_fn_t)(const KParams);
 
-template <typename OUT, int MAXT>
+// phase 0 = the whole step in one launch; 1 / 2 = its two halves (single-warp envs)
+template <typename OUT, int MAXT, int PH>
 step_fn_t pick2(bool dyn, bool emit) {
-    if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, MAXT> : (step_fn_t)k_step<OUT, true, false, MAXT>;
-    return emit ? (step_fn_t)k_step<OUT, false, true, MAXT> : (step_fn_t)k_step<OUT, false, false, MAXT>;
+    if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, MAXT, PH> : (step_fn_t)k_step<OUT, true, false, MAXT, PH>;
+    return emit ? (step_fn_t)k_step<OUT, false, true, MAXT, PH> : (step_fn_t)k_step<OUT, false, false, MAXT, PH>;
 }
-step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt) {
-    if (nt <= 128) return f32 ? pick2<float, 128>(dyn, emit) : pick2<double, 128>(dyn, emit);
-    return f32 ? pick2<float, 1024>(dyn, emit) : pick2<double, 1024>(dyn, emit);
+step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt, int phase = 0) {
+    if (nt <= 128) {
+        if (phase == 1) return f32 ? pick2<float, 128, 1>(dyn, emit) : pick2<double, 128, 1>(dyn, emit);
+        if (phase == 2) return f32 ? pick2<float, 128, 2>(false, emit) : pick2<double, 128, 2>(false, emit);
+        return f32 ? pick2<float, 128, 0>(dyn, emit) : pick2<double, 128, 0>(dyn, emit);
+    }
+    return f32 ? pick2<float, 1024, 0>(dyn, emit) : pick2<double, 1024, 0>(dyn, emit);
 }
 
 void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool self_state, bool want_prior,
@@ -106,6 +111,7 @@ struct swarm_sim {
     swarm_buffers buf;
     KParams K;
     int nt;                 // threads per CTA
+    bool split;             // step = two launches (k_step PH 1 + PH 2)
     size_t smem;
     int pending;            // a_prior buffer holding the prior of the CURRENT state
     int last;               // a_prior buffer returned by the most recent step
@@ -179,11 +185,14 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
         delete s;
         return fail(SWARM_ERR_UNSUPPORTED, "n_a x n_g_max needs more shared memory than one SM has");
     }
-    for (int dyn = 0; dyn < 2; ++dyn) {
-        step_fn_t f = pick_step(cfg->out_dtype == SWARM_F32, dyn != 0, cfg->emit_indices != 0, s->nt);
-        cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
-        if (e != cudaSuccess) { delete s; return fail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
-    }
+    s->split = (s->nt == 32) && !getenv("SWARM_FUSED_STEP");      // single-warp envs: two launches per step (see k_step, PH)
+    for (int dyn = 0; dyn < 2; ++dyn)
+        for (int ph = 0; ph < 3; ++ph) {
+            if (ph > 0 && s->nt > 128) continue;
+            step_fn_t f = pick_step(cfg->out_dtype == SWARM_F32, dyn != 0, cfg->emit_indices != 0, s->nt, ph);
+            cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+            if (e != cudaSuccess) { delete s; return fail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+        }
     s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
     s->d_stage = nullptr; s->stage_cap = 0; s->d_act = nullptr; s->act_cap = 0;
     s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
@@ -305,10 +314,16 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     KParams K = s->K;
     K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
     K.prior_next = s->buf.a_prior[dyn ? (1 - s->pending) : s->pending];
-    step_fn_t f = pick_step(s->cfg.out_dtype == SWARM_F32, dyn, s->cfg.emit_indices != 0, s->nt);
-    f<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+    const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
+    if (s->split) {
+        pick_step(f32, dyn, emit, s->nt, 1)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+        pick_step(f32, dyn, emit, s->nt, 2)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+        s->launches += 2;
+    } else {
+        pick_step(f32, dyn, emit, s->nt, 0)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+        s->launches++;
+    }
     CU_TRY(cudaGetLastError());
-    s->launches++;
     return SWARM_OK;
 }
 
