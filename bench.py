@@ -208,6 +208,7 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
     pol = DevicePolicy(D, A, H, noise_scale=0.5).load_state_dict(sd)
     buf = ReplayBufferAgent(4, E * n_a, slice(0, n_a), D, A)
     obs_prev, act2 = sim.obs.clone(), torch.empty_like(act)
+    obs_pair = [sim.obs, torch.empty_like(sim.obs)]
     idx = slice(0, n_a)
     rows = E * n_a
     push_ms = timed(lambda: buf.push(obs_prev, act, sim.reward, sim.obs, sim.done, idx, sim.a_prior), 10)
@@ -216,11 +217,13 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
     pol.set_precision("f16_tc")
     pol_tc_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 20)
 
-    def loop_step():
-        _, lp = pol.step(obs_prev, explore=True, out=act2)
+    def loop_step():                       # the simulator's obs output alternates between two buffers: no copy
+        prev, spare = obs_pair
+        _, lp = pol.step(prev, explore=True, out=act2)
+        sim.set_obs_buffer(spare)
         nxt, rew, done, _, prior = sim.step(act2)
-        buf.push(obs_prev, act2, rew, nxt, done, idx, prior, lp)
-        obs_prev.copy_(nxt)
+        buf.push(prev, act2, rew, nxt, done, idx, prior, lp)
+        obs_pair[0], obs_pair[1] = spare, prev
     loop_ms = timed(loop_step, 20)
     flop = 2.0 * rows * (D * H + 2 * H * H + H * A)
     return {
@@ -228,7 +231,7 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
                          "frac_of_hbm_peak": push_bytes / push_ms / 1e6 / hbm_peak, "rows": rows},
         "policy_fp32": {"kernel": "swarm::k_policy_mlp", "ms": pol_fp32_ms, "TFLOPs": flop / pol_fp32_ms / 1e9},
         "policy_f16_tc": {"kernel": "swarm::k_policy_mlp_tc (tcgen05, TMEM)", "ms": pol_tc_ms, "TFLOPs": flop / pol_tc_ms / 1e9},
-        "device_rollout_loop": {"stages": "policy(f16_tc) -> step -> push -> obs copy", "ms_per_step": loop_ms,
+        "device_rollout_loop": {"stages": "policy(f16_tc) -> step -> push, obs double-buffered", "ms_per_step": loop_ms,
                                 "agent_steps_per_s": rows / loop_ms * 1e3},
     }
 

@@ -172,6 +172,11 @@ int swarm_reset(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_of
  * {coverage_rate, distribution_uniformity, voronoi_based_uniformity} (assembly_wrapper.py:48-72, 74-101, 103-129). */
 int swarm_metrics(swarm_sim *sim, double *out_dev, void *stream);
 
+/* Redirect the observation output of the following observe / step calls to another device buffer of the same shape and
+ * dtype.  Lets a device-resident rollout loop keep the previous observation (policy input, replay `obs`) and the new one
+ * (replay `next_obs`) without a copy: alternate two buffers. */
+int swarm_set_obs_buffer(swarm_sim *sim, void *obs_dev);
+
 /* Tell the handle that the caller overwrote p / dp (device buffers) outside step(): the next step recomputes the
  * prior from the new state and the stale neighbor_index, exactly like the reference would (ENV:613-624). */
 int swarm_mark_state_dirty(swarm_sim *sim);

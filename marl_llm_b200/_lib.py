@@ -39,7 +39,7 @@ class SwarmBuffers(C.Structure):
 # every symbol include/swarm_b200.h declares (tests check the library exports all of them)
 LEGACY_SYMBOLS = ["_get_observation", "_get_reward", "_sf_b2b_all", "_get_dist_b2w", "calculateActionPrior"]
 BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_destroy", "swarm_set_grid",
-                   "swarm_set_shapes", "swarm_reset", "swarm_metrics",
+                   "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer",
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold"]
@@ -82,6 +82,7 @@ def load():
     lib.swarm_destroy.argtypes = [C.c_void_p]
     lib.swarm_set_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_mark_state_dirty.argtypes = [C.c_void_p]
+    lib.swarm_set_obs_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.swarm_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_set_shapes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]

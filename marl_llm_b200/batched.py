@@ -190,6 +190,13 @@ class BatchedAssemblySim:
         self.dp.copy_(torch.as_tensor(dp, dtype=torch.float64).reshape(self.E, 2, self.n_a))
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
 
+    def set_obs_buffer(self, obs):
+        """Redirect the observation output of the following observe()/step() calls to `obs` (same shape / dtype, CUDA,
+        contiguous); `self.obs` then refers to it.  Alternate two buffers to keep the previous observation without a copy."""
+        assert obs.is_cuda and obs.is_contiguous() and obs.shape == self.obs.shape and obs.dtype == self.obs.dtype
+        check(self.lib.swarm_set_obs_buffer(self._h, C.c_void_p(obs.data_ptr())), "swarm_set_obs_buffer")
+        self.obs = obs
+
     def mark_state_dirty(self):
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
 

@@ -304,6 +304,12 @@ int swarm_metrics(swarm_sim *s, double *out_dev, void *stream) {
     return SWARM_OK;
 }
 
+int swarm_set_obs_buffer(swarm_sim *s, void *obs_dev) {
+    if (!s || !obs_dev) return fail(SWARM_ERR_INVALID, "null argument");
+    s->buf.obs = obs_dev; s->K.obs = obs_dev;
+    return SWARM_OK;
+}
+
 int swarm_mark_state_dirty(swarm_sim *s) {
     if (!s) return fail(SWARM_ERR_INVALID, "null handle");
     s->prior_dirty = true;

@@ -8,22 +8,24 @@ inside the loop; per-step statistics stay on the device until the caller asks fo
         buffer.push(obs, actions, rew, next_obs, done, index, prior)     TRAIN:105-106
         obs = next_obs                                      TRAIN:107
 
-The simulator owns ONE observation buffer, so the loop keeps the previous observation in a second tensor (a device copy
-per step; the push kernel reads both)."""
+The previous observation (policy input, replay `obs`) must outlive the step that produces the next one, so the simulator's
+observation output alternates between two device buffers (`sim.set_obs_buffer`): no copy."""
 import torch
 
 
 def rollout(sim, policy, buffer, steps, explore=True, index=None):
     """Runs `steps` environment steps from the simulator's current observation.  Returns the per-step mean reward
-    ([steps] float64 CUDA tensor; TRAIN:110 accumulates np.mean(rewards) per step)."""
+    ([steps] float64 CUDA tensor; TRAIN:110 accumulates np.mean(rewards) per step).  On return `sim.obs` is the last
+    observation (it may be either of the two buffers)."""
     index = index if index is not None else slice(0, sim.n_a)
-    obs_prev = sim.obs.clone()
+    obs_prev, spare = sim.obs, torch.empty_like(sim.obs)
     act = torch.empty(sim.E, policy.act_dim, sim.n_a, dtype=torch.float32, device=sim.device)
     mean_rew = torch.zeros(steps, dtype=torch.float64, device=sim.device)
     for t in range(steps):
         _, log_pi = policy.step(obs_prev, explore=explore, out=act)
+        sim.set_obs_buffer(spare)
         next_obs, rew, done, _, prior = sim.step(act)
         buffer.push(obs_prev, act, rew, next_obs, done, index, prior, log_pi)
         mean_rew[t] = rew.double().mean()
-        obs_prev.copy_(next_obs)
+        obs_prev, spare = next_obs, obs_prev
     return mean_rew

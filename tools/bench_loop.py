@@ -24,11 +24,14 @@ pol = DevicePolicy(D, A, H, precision=prec, noise_scale=0.5).load_state_dict(sd)
 buf = ReplayBufferAgent(8, E * n_a, slice(0, n_a), D, A)       # 8 steps of history: 8 x 1.97M rows (24 GB)
 obs_prev = sim.obs.clone(); act = torch.empty(E, A, n_a, device="cuda")
 idx = slice(0, n_a)
+pair = [sim.obs, torch.empty_like(sim.obs)]
 def one():
-    _, lp = pol.step(obs_prev, explore=True, out=act)
+    prev, spare = pair
+    _, lp = pol.step(prev, explore=True, out=act)
+    sim.set_obs_buffer(spare)
     nxt, rew, done, _, prior = sim.step(act)
-    buf.push(obs_prev, act, rew, nxt, done, idx, prior, lp)
-    obs_prev.copy_(nxt)
+    buf.push(prev, act, rew, nxt, done, idx, prior, lp)
+    pair[0], pair[1] = spare, prev
 for _ in range(20): one()
 torch.cuda.synchronize()
 K = 50
@@ -37,5 +40,5 @@ e0.record()
 for _ in range(K): one()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(json.dumps({"loop": "policy(%s) -> step -> push -> copy" % prec, "envs": E, "n_a": n_a, "ms_per_step": ms,
+print(json.dumps({"loop": "policy(%s) -> step -> push (obs double-buffered)" % prec, "envs": E, "n_a": n_a, "ms_per_step": ms,
                   "agent_steps_per_s": E * n_a / ms * 1e3, "mean_reward": float(sim.reward.mean())}))
