@@ -5,6 +5,7 @@
 #include "swarm_kernels.cuh"
 #include "../../include/swarm_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,7 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
     b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
+    b += (size_t)nt * sizeof(float2);                                                                // fp32 positions (pair-loop filter)
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
     if (nt == 32 && n_words <= 32 && scratch > (size_t)2 * CHUNK_CELLS * sizeof(double2)) b += scratch;   // aliases the TMA ring when it fits
     return b;
@@ -100,6 +102,11 @@ void fill_constants(KParams &K, int n_a, int n_g_max, int n_obs, int n_occ, bool
     K.U_occ = thresh_le(r_avoid / 2.0);                                   // CPP:185
     K.T_avoid = thresh_lt(r_avoid);                                       // CPP:482, 1166
     K.Tsen_f = std::nextafterf((float)(K.T_sen * (double)SLACK_REL + (double)SLACK_ABS), INFINITY);   // box test threshold
+    // fp32 filter of the agent-pair loops: exact squared distance <= T  =>  fp32 squared distance <= T * (1 + 1e-4) + 1e-5
+    // for |coordinates| < 16 (rounding of the positions to fp32: 2 * 16 * 2^-24 per difference, see k_step)
+    auto pair_filter_threshold = [](double T) { return std::nextafterf((float)(T * 1.0001 + 1e-5), INFINITY); };
+    K.Tcol_f = pair_filter_threshold(K.T_col);
+    K.Tpair_f = pair_filter_threshold(std::max(K.T_sen, K.T_near_hi));
 }
 
 double in_shape_thresh(double l_cell) { return thresh_lt(std::sqrt(2.0) * l_cell / 2); }   // CPP:889
