@@ -57,7 +57,7 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     if (e != cudaSuccess) { delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     if (e == cudaSuccess) e = cudaMalloc(&p->d_w16, (size_t)3 * TC_W_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
     if (e != cudaSuccess) { cudaFree(p->d_w); cudaFree(p->d_w16); delete p; return pfail(SWARM_ERR_CUDA, std::string("policy setup: ") + cudaGetErrorString(e)); }
     *out = p;
     return SWARM_OK;
@@ -128,7 +128,7 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
         Q.base = P; Q.w16 = p->d_w16; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
         Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
         const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
-        k_policy_mlp_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(Q);
+        k_policy_mlp_tc<<<grid, TC_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
         PCU_TRY(cudaGetLastError());
         p->launches++;
         return SWARM_OK;
@@ -142,6 +142,8 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
 
 int swarm_policy_set_precision(swarm_policy *p, int precision) {
     if (!p || (precision != SWARM_POLICY_FP32 && precision != SWARM_POLICY_F16_TC)) return pfail(SWARM_ERR_INVALID, "bad precision");
+    if (precision == SWARM_POLICY_F16_TC && p->act_dim > TC_AMAX)
+        return pfail(SWARM_ERR_UNSUPPORTED, "the tensor-core policy path supports act_dim <= 4 (shared-memory budget)");
     p->precision = precision;
     return SWARM_OK;
 }

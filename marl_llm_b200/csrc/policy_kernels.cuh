@@ -202,7 +202,10 @@ constexpr int TC_SBO = 128;                                 // bytes between 8-r
 constexpr int TC_COL_D = 0, TC_COL_A = 256, TC_COLS = 512;  // TMEM columns: accumulator [0,192), operand A [256,352)
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = 192, M = 128
 constexpr uint32_t TC_IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-constexpr size_t TC_SMEM = (size_t)3 * TC_W_BYTES + 3 * POL_HP * 4 + (size_t)POL_AMAX * POL_HP * 4 + POL_AMAX * 4 + 96;
+constexpr int TC_AMAX = 4;                                  // largest action dimension of the tensor-core path (shared-memory budget)
+__host__ __device__ constexpr size_t tc_smem_bytes(int A) {  // weights + biases + output layer + partial outputs + barriers
+    return (size_t)3 * TC_W_BYTES + 3 * POL_HP * 4 + (size_t)A * POL_HP * 4 + (size_t)((A + 1) & ~1) * 4 + (size_t)TC_M * A * 4 + 96;
+}
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -243,7 +246,9 @@ struct PolicyTcParams {
 };
 
 constexpr int TC_LOADERS = 2;               // loader warps per TMEM lane quadrant (each converts 192 / TC_LOADERS features of a row)
-constexpr int TC_THREADS = (1 + TC_LOADERS) * TC_M;   // warps 0-3: MMA issue + epilogues ("compute");  warps 4..: observation loaders
+constexpr int TC_EPI = 2;                   // epilogue warps per TMEM lane quadrant (each handles 192 / TC_EPI accumulator columns of a row)
+constexpr int TC_CTHREADS = TC_EPI * TC_M;  // warps 0-7: MMA issue (thread 0) + epilogues ("compute")
+constexpr int TC_THREADS = (TC_EPI + TC_LOADERS) * TC_M;   // warps 8-15: observation loaders
 constexpr int TC_COL_A1 = TC_COL_A + POL_HP / 2;   // second operand-A buffer (the loader fills one while the other is in use)
 
 __device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
@@ -260,9 +265,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
     extern __shared__ __align__(128) unsigned char tsm[];
     unsigned char *sW = tsm;                                             // 3 layers of weights
     float *sB = reinterpret_cast<float *>(sW + 3 * TC_W_BYTES);          // [3][192]
-    float *sW4 = sB + 3 * POL_HP;                                        // [AMAX][192]
-    float *sb4 = sW4 + POL_AMAX * POL_HP;                                // [AMAX]
-    uint64_t *bar_w = reinterpret_cast<uint64_t *>(sb4 + POL_AMAX);      // weights landed
+    float *sW4 = sB + 3 * POL_HP;                                        // [A][192]
+    float *sb4 = sW4 + Q.base.A * POL_HP;                                // [A], padded to an even count
+    float *s_part = sb4 + ((Q.base.A + 1) & ~1);                         // [TC_M][A] partial outputs of the second column half
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(s_part + TC_M * Q.base.A);   // weights landed
     uint64_t *bar_mma = bar_w + 1;                                       // a layer's MMAs retired
     uint64_t *bar_full = bar_mma + 1;                                    // [2] loader -> compute: operand-A buffer b holds a tile's observations
     uint64_t *bar_free = bar_full + 2;                                   // [2] compute -> loader: the last MMA reading buffer b has retired
@@ -298,13 +304,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches the TMEM lane quadrant warp % 4
     const int row = tid & (TC_M - 1);                                    // TMEM lane = agent of the tile
 
-    if (warp >= 4) {
+    if (warp >= 4 * TC_EPI) {
         // ================= loader: observation row -> fp16 -> operand-A buffer (it & 1), one tile ahead of the MMAs
         int it = 0;
 #pragma unroll 1
         for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
-            if (tid == TC_M) {  // pull the NEXT tile's observations (a contiguous run of whole envs) into the L2 while this one is converted
+            if (tid == TC_CTHREADS) {  // pull the NEXT tile's observations (a contiguous run of whole envs) into the L2 while this one is converted
                 const long nt = tile + gridDim.x;
                 if (nt < Q.n_tiles) {
                     const long e0 = nt * TC_M / n_a;
@@ -326,9 +332,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
             const float *orow = P.obs + e * (long)P.K0 * n_a + ag;
             const uint32_t abase = lane_base + (b ? TC_COL_A1 : TC_COL_A);
             constexpr int FPL = POL_HP / TC_LOADERS;                     // features per loader thread
-            const int k_lo = ((warp - 4) >> 2) * FPL;
-#pragma unroll
-            for (int c = 0; c < FPL / 32; ++c) {                         // fully unrolled: all FPL loads of the row are in flight together
+            const int k_lo = ((warp - 4 * TC_EPI) >> 2) * FPL;
+#pragma unroll 1
+            for (int c = 0; c < FPL / 32; ++c) {                         // 32 loads in flight per thread and batch (register budget: 512 threads)
                 float f[32];
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
@@ -345,7 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
             tc_mbar_arrive(&bar_full[b]);
         }
     } else {
-        // ================= compute: thread 0 issues the MMAs, all four warps run the epilogues
+        // ================= compute: thread 0 issues the MMAs; two warps per lane quadrant share a row's epilogue (96 columns each)
+        const int half = warp >> 2;
         uint32_t par_mma = 0;
         int it = 0;
 #pragma unroll 1
@@ -355,14 +362,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
             const long col = tile * TC_M + row;
             const bool valid = col < P.n_cols;
             const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
-            float out[POL_AMAX];
+            float out[TC_AMAX];
 #pragma unroll
-            for (int j = 0; j < POL_AMAX; ++j) out[j] = 0.f;
+            for (int j = 0; j < TC_AMAX; ++j) out[j] = 0.f;
 #pragma unroll 1
             for (int layer = 0; layer < 3; ++layer) {
                 if (layer > 0) {                                         // operand A rewritten by every epilogue thread
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory");
                 }
                 if (tid == 0) {
                     if (it == 0 && layer == 0) tc_mbar_wait(bar_w, 0);
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const float *bias = sB + layer * POL_HP;
 #pragma unroll 1
-                for (int c = 0; c < POL_HP / 32; ++c) {                  // 32 accumulator columns at a time
+                for (int c = half * (POL_HP / 32 / TC_EPI); c < (half + 1) * (POL_HP / 32 / TC_EPI); ++c) {   // 32 accumulator columns at a time
                     uint32_t v[32];
                     TC_LD32(lane_base + TC_COL_D + c * 32, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                         TC_ST16(lane_base + acol + c * 16, r);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < POL_AMAX; ++j) {
+                        for (int j = 0; j < TC_AMAX; ++j) {
                             if (j < A) {
                                 float s_ = out[j];
 #pragma unroll
@@ -427,16 +434,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                 }
                 if (layer < 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             }
+            if (half == 1) {                                             // the first half finishes the row
+#pragma unroll
+                for (int j = 0; j < TC_AMAX; ++j) if (j < A) s_part[row * A + j] = out[j];
+            }
             // every compute thread has read its accumulator row before thread 0 may start the next tile's first MMA
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory");
             // ---- tanh, exploration, outputs (same definitions as k_policy_mlp)
-            if (valid) {
+            if (valid && half == 0) {
                 float q2 = 0.f;
 #pragma unroll
-                for (int j = 0; j < POL_AMAX; ++j) {
+                for (int j = 0; j < TC_AMAX; ++j) {
                     if (j >= A) break;
-                    float a = tanhf(out[j] + sb4[j]);
+                    float a = tanhf((out[j] + s_part[row * A + j]) + sb4[j]);
                     if (P.explore == 1) {
                         const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
                         const float u1 = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);
