@@ -84,7 +84,8 @@ def compare_all(sim, ob, t, fields=("p", "dp", "obs", "reward", "a_prior", "nbr"
 
 
 @pytest.mark.parametrize("n_a,E,steps,mode", [(30, 256, 200, "mixed"), (30, 64, 200, "goal"), (7, 64, 60, "goal"),
-                                              (33, 32, 60, "goal"), (100, 16, 40, "goal"), (1, 8, 10, "random")])
+                                              (33, 32, 60, "goal"), (100, 16, 40, "goal"), (1, 8, 10, "random"),
+                                              (32, 16, 40, "goal"), (31, 16, 40, "mixed")])
 def test_batch_vs_oracle_every_step(n_a, E, steps, mode):
     """Seeded batch, every output of every step compared with the oracle (parity layout: fp64 + index arrays).
     'goal' drives agents into the shapes so the in-shape / occupancy / 80-cell subsample / reward branches run."""
@@ -430,3 +431,43 @@ def test_every_output_element_is_rewritten_each_step(emit):
             assert np.array_equal(sim.sensed_index.cpu().numpy(), ob.sensed_index), t
             assert np.array_equal(sim.occupied_index.cpu().numpy(), ob.occupied_index), t
     assert ob.in_flags.sum() > 100 and ob.reward.sum() > 0
+
+
+def test_two_launch_step_equals_fused_step(monkeypatch):
+    """Single-warp envs run the step as two launches (k_step PH 1 + PH 2); SWARM_FUSED_STEP=1 keeps the one-launch kernel.
+    Same inputs -> identical state, outputs and index arrays, every step (both layouts of the emission: parity + production)."""
+    E, n_a = 96, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=55)
+    ngm = int(shapes["n_g"].max())
+    sims = []
+    for fused in (False, True):
+        if fused:
+            monkeypatch.setenv("SWARM_FUSED_STEP", "1")
+        else:
+            monkeypatch.delenv("SWARM_FUSED_STEP", raising=False)
+        pair = [make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True),
+                make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32, emit_indices=False)]
+        sims.append(pair)
+    monkeypatch.delenv("SWARM_FUSED_STEP", raising=False)
+    ob = orc.OracleBatch(params, nthreads=8)
+    for pair in sims:
+        for s_ in pair:
+            load_batch(s_, ob, params, grids, P, DP)
+            s_.observe()
+    ob.observe()
+    rng = np.random.RandomState(2)
+    l0 = [[s_.launch_count for s_ in pair] for pair in sims]
+    for t in range(50):
+        a = goal_seeking_action(ob.obs, ob.dp, rng) if t % 2 else rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        ta = torch.from_numpy(a).cuda()
+        for pair in sims:
+            for s_ in pair:
+                s_.step(ta)
+        ob.step(a)
+        for k in range(2):
+            a_, b_ = sims[0][k], sims[1][k]
+            for name in ("p", "dp", "obs", "reward", "a_prior", "neighbor_index", "in_flags", "nearest_cell"):
+                assert torch.equal(getattr(a_, name), getattr(b_, name)), (name, t, k)
+        assert torch.equal(sims[0][0].sensed_index, sims[1][0].sensed_index) and torch.equal(sims[0][0].occupied_index, sims[1][0].occupied_index)
+        assert np.array_equal(sims[0][0].obs.cpu().numpy(), ob.obs), t
+    assert sims[0][0].launch_count - l0[0][0] == 100 and sims[1][0].launch_count - l0[1][0] == 50
