@@ -112,3 +112,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_rollout_and_policy_entry_points_fail_loudly_without_gpu(lib):
+    """Groups 3 and 4 of the ABI: argument validation happens before any device access; on a box without a GPU the
+    policy constructor reports SWARM_ERR_NO_DEVICE (there is no CPU implementation behind it)."""
+    import torch
+    b = _lib.SwarmRolloutBuffers()
+    b.struct_size = 0
+    rc = lib.swarm_rollout_push(C.byref(b), 0, 1, 1, 0, 1, None, None, None, None, None, _lib.SWARM_F32, None, _lib.SWARM_F32, None, None)
+    assert rc == _lib.SWARM_ERR_INVALID and b"struct_size" in lib.swarm_last_error()
+    b.struct_size = C.sizeof(_lib.SwarmRolloutBuffers)
+    b.obs_dim, b.act_dim, b.capacity = 192, 2, 100
+    rc = lib.swarm_rollout_push(C.byref(b), 0, 1, 1, 0, 1, None, None, None, None, None, _lib.SWARM_F32, None, _lib.SWARM_F32, None, None)
+    assert rc == _lib.SWARM_ERR_INVALID and b"NULL" in lib.swarm_last_error()
+    rc = lib.swarm_rollout_gather(C.byref(b), None, 4, None, None, None, None, None, None, None, None)
+    assert rc == _lib.SWARM_ERR_INVALID
+    h = C.c_void_p()
+    assert lib.swarm_policy_create(0, 500, 180, 2, C.byref(h)) == _lib.SWARM_ERR_UNSUPPORTED        # obs_dim > 192
+    assert lib.swarm_policy_create(0, 192, 180, 9, C.byref(h)) == _lib.SWARM_ERR_UNSUPPORTED        # act_dim > 8
+    if not torch.cuda.is_available():
+        assert lib.swarm_policy_create(0, 192, 180, 2, C.byref(h)) == _lib.SWARM_ERR_NO_DEVICE
+        assert b"no CPU fallback" in lib.swarm_last_error()
+        from marl_llm_b200.policy import DevicePolicy
+        from marl_llm_b200.rollout import ReplayBufferAgent
+        with pytest.raises(_lib.SwarmError):
+            DevicePolicy(192, 2)
+        with pytest.raises(_lib.SwarmError):
+            ReplayBufferAgent(10, 30, slice(0, 30), 192, 2)
+    assert lib.swarm_policy_step(None, None, 1, 1, None, None, 0, 0.1, 0, 0, None) == _lib.SWARM_ERR_INVALID
+    assert lib.swarm_policy_set_precision(None, 0) == _lib.SWARM_ERR_INVALID
+
+
+def test_rollout_struct_mirror_matches_header():
+    hdr = open(os.path.join(REPO, "include", "swarm_b200.h")).read()
+    body = re.search(r"typedef struct swarm_rollout_buffers \{(.*?)\} swarm_rollout_buffers;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n for decl in body.split(";") for n in re.findall(r"\*?\s*([a-z_0-9]+)\s*(?:,|$)", decl.split(None, 1)[1] if decl.strip() else "")]
+    assert names == [f[0] for f in _lib.SwarmRolloutBuffers._fields_], names
