@@ -214,6 +214,8 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
     push_ms = timed(lambda: buf.push(obs_prev, act, sim.reward, sim.obs, sim.done, idx, sim.a_prior), 10)
     push_bytes = rows * (2 * D * 4 * 2 + 2 * A * 4 * 2 + 4 * 2 + 1 + 4)
     pol_fp32_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 3)
+    pol.set_precision("f16x3_tc")
+    pol_tc3_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 20)
     pol.set_precision("f16_tc")
     pol_tc_ms = timed(lambda: pol.step(obs_prev, explore=True, out=act2, want_log_pi=False), 20)
 
@@ -230,6 +232,8 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
         "rollout_push": {"kernel": "swarm::k_rollout_push_tma", "ms": push_ms, "GBps": push_bytes / push_ms / 1e6,
                          "frac_of_hbm_peak": push_bytes / push_ms / 1e6 / hbm_peak, "rows": rows},
         "policy_fp32": {"kernel": "swarm::k_policy_mlp", "ms": pol_fp32_ms, "TFLOPs": flop / pol_fp32_ms / 1e9},
+        "policy_f16x3_tc": {"kernel": "swarm::k_policy_mlp_tc3 (tcgen05, fp16 hi/lo split, fp32-accurate)", "ms": pol_tc3_ms,
+                            "TFLOPs_useful": flop / pol_tc3_ms / 1e9, "TFLOPs_issued": 3 * flop / pol_tc3_ms / 1e9},
         "policy_f16_tc": {"kernel": "swarm::k_policy_mlp_tc (tcgen05, TMEM)", "ms": pol_tc_ms, "TFLOPs": flop / pol_tc_ms / 1e9},
         "device_rollout_loop": {"stages": "policy(f16_tc) -> step -> push, obs double-buffered", "ms_per_step": loop_ms,
                                 "agent_steps_per_s": rows / loop_ms * 1e3},

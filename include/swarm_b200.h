@@ -259,6 +259,10 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
  * accumulators in tensor memory); ~50x faster, deviates by ~1e-3 absolute on the tanh output. */
 #define SWARM_POLICY_FP32 0
 #define SWARM_POLICY_F16_TC 1
+/* SWARM_POLICY_F16X3_TC: fp32-accurate tensor-core path: every operand is split into two fp16 numbers (hi + lo, 22 bits),
+ * three tcgen05.mma per k-step (hi*hi + lo*hi + hi*lo) into one fp32 accumulator, weights streamed through a 3-slot
+ * shared-memory ring.  Agrees with the fp32 network to ~1e-6 (|values| must stay below 65504). */
+#define SWARM_POLICY_F16X3_TC 2
 int swarm_policy_set_precision(swarm_policy *p, int precision);
 /* test hook: when non-NULL, the tensor-core path also writes its layer-1 accumulators (fc1 without bias) to
  * layer1_acc_dev [E*n_a][192] f32 (device). */

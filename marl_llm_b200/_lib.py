@@ -46,7 +46,7 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
                   "swarm_policy_set_precision", "swarm_policy_debug_buffer"]
-SWARM_POLICY_FP32, SWARM_POLICY_F16_TC = 0, 1
+SWARM_POLICY_FP32, SWARM_POLICY_F16_TC, SWARM_POLICY_F16X3_TC = 0, 1, 2
 
 
 class SwarmRolloutBuffers(C.Structure):

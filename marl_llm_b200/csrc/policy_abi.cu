@@ -25,6 +25,7 @@ struct swarm_policy {
     int device, obs_dim, hidden, act_dim;
     float *d_w;          // one allocation: Wt[3][HP][HP], b[3][HP], W4[A][HP], b4[A]
     unsigned char *d_w16; // [3][TC_W_BYTES] fp16 weights in the canonical UMMA K-major layout (tensor-core path)
+    unsigned char *d_w16x; // [6][TC_W_BYTES] hi/lo fp16 split of the weights, chunk order H1 L1 H2 L2 H3 L3 (fp32-accurate tensor-core path)
     int precision;       // SWARM_POLICY_FP32 | SWARM_POLICY_F16_TC
     int n_sm;
     float *debug;        // test hook: layer-1 accumulators of the tensor-core path
@@ -45,7 +46,7 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     PCU_TRY(cudaSetDevice(device));
     swarm_policy *p = new swarm_policy();
     p->device = device; p->obs_dim = obs_dim; p->hidden = hidden_dim; p->act_dim = act_dim; p->loaded = false; p->launches = 0;
-    p->precision = SWARM_POLICY_FP32; p->debug = nullptr; p->d_w16 = nullptr;
+    p->precision = SWARM_POLICY_FP32; p->debug = nullptr; p->d_w16 = nullptr; p->d_w16x = nullptr;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
         delete p;
@@ -56,9 +57,11 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     cudaError_t e = cudaMalloc(&p->d_w, n * sizeof(float));
     if (e != cudaSuccess) { delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     if (e == cudaSuccess) e = cudaMalloc(&p->d_w16, (size_t)3 * TC_W_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_w16x, (size_t)6 * TC_W_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
     if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
-    if (e != cudaSuccess) { cudaFree(p->d_w); cudaFree(p->d_w16); delete p; return pfail(SWARM_ERR_CUDA, std::string("policy setup: ") + cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { cudaFree(p->d_w); cudaFree(p->d_w16); cudaFree(p->d_w16x); delete p; return pfail(SWARM_ERR_CUDA, std::string("policy setup: ") + cudaGetErrorString(e)); }
     *out = p;
     return SWARM_OK;
 }
@@ -68,6 +71,7 @@ int swarm_policy_destroy(swarm_policy *p) {
     cudaSetDevice(p->device);
     cudaFree(p->d_w);
     cudaFree(p->d_w16);
+    cudaFree(p->d_w16x);
     delete p;
     return SWARM_OK;
 }
@@ -103,6 +107,20 @@ int swarm_policy_load(swarm_policy *p, const float *w1, const float *b1, const f
                 h16[(size_t)l * POL_HP * POL_HP + byte / 2] = __float2half_rn(W[l][(size_t)nn * Kin[l] + k]);
             }
     PCU_TRY(cudaMemcpy(p->d_w16, h16.data(), (size_t)3 * TC_W_BYTES, cudaMemcpyHostToDevice));
+    // fp32-accurate tensor-core path: w = hi + lo with hi = fp16(w), lo = fp16(w - hi); same layout, chunks H1 L1 H2 L2 H3 L3
+    std::vector<__half> hx((size_t)6 * POL_HP * POL_HP, __float2half(0.f));
+    for (int l = 0; l < 3; ++l)
+        for (int nn = 0; nn < H; ++nn)
+            for (int k = 0; k < Kin[l]; ++k) {
+                const size_t byte = (size_t)(k / 8) * TC_LBO + (size_t)(nn / 8) * TC_SBO + (size_t)(nn % 8) * 16 + (size_t)(k % 8) * 2;
+                float w = W[l][(size_t)nn * Kin[l] + k];
+                w = w > 65504.f ? 65504.f : (w < -65504.f ? -65504.f : w);
+                const __half hi = __float2half_rn(w);
+                const __half lo = __float2half_rn(w - __half2float(hi));
+                hx[(size_t)(2 * l) * POL_HP * POL_HP + byte / 2] = hi;
+                hx[(size_t)(2 * l + 1) * POL_HP * POL_HP + byte / 2] = lo;
+            }
+    PCU_TRY(cudaMemcpy(p->d_w16x, hx.data(), (size_t)6 * TC_W_BYTES, cudaMemcpyHostToDevice));
     p->loaded = true;
     return SWARM_OK;
 }
@@ -123,6 +141,16 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
     P.W4 = p->d_w + (size_t)3 * POL_HP * POL_HP + 3 * POL_HP;
     P.b4 = P.W4 + (size_t)p->act_dim * POL_HP;
     P.slope = 0.01f; P.explore = explore; P.scale = noise_scale; P.seed = seed; P.step = step;
+    if (p->precision == SWARM_POLICY_F16X3_TC) {
+        PolicyTcParams Q;
+        Q.base = P; Q.w16 = p->d_w16x; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
+        Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
+        const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
+        k_policy_mlp_tc3<<<grid, T3_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
+        PCU_TRY(cudaGetLastError());
+        p->launches++;
+        return SWARM_OK;
+    }
     if (p->precision == SWARM_POLICY_F16_TC) {
         PolicyTcParams Q;
         Q.base = P; Q.w16 = p->d_w16; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
@@ -141,8 +169,9 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
 }
 
 int swarm_policy_set_precision(swarm_policy *p, int precision) {
-    if (!p || (precision != SWARM_POLICY_FP32 && precision != SWARM_POLICY_F16_TC)) return pfail(SWARM_ERR_INVALID, "bad precision");
-    if (precision == SWARM_POLICY_F16_TC && p->act_dim > TC_AMAX)
+    if (!p || (precision != SWARM_POLICY_FP32 && precision != SWARM_POLICY_F16_TC && precision != SWARM_POLICY_F16X3_TC))
+        return pfail(SWARM_ERR_INVALID, "bad precision");
+    if (precision != SWARM_POLICY_FP32 && p->act_dim > TC_AMAX)
         return pfail(SWARM_ERR_UNSUPPORTED, "the tensor-core policy path supports act_dim <= 4 (shared-memory budget)");
     p->precision = precision;
     return SWARM_OK;

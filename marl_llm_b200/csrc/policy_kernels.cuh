@@ -475,4 +475,257 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_COLS) : "memory");
 }
 
+// =====================================================================================================
+// fp32-accurate tensor-core path: every fp32 operand x is split into two fp16 numbers, hi = fp16(x) and lo = fp16(x - hi)
+// (22 significant bits together; fp16 x fp16 products are exact in the fp32 accumulator), and each layer runs
+//     D  =  A_hi W_hi^T  +  A_lo W_hi^T  +  A_hi W_lo^T          (the lo x lo term, 2^-22 relative, is dropped)
+// as 3 x 12 tcgen05.mma into ONE fp32 accumulator.  Weights are now 2 x 73 728 B per layer, so they cannot all stay
+// resident: a dedicated producer warp streams the six chunks H1 L1 H2 L2 H3 L3 (L2-resident) round and round through a
+// 3-slot shared-memory ring with bulk async copies; full[slot] (expect_tx) tells the MMA thread a chunk has landed,
+// free[slot] (tcgen05.commit after the last MMA reading it) tells the producer it may be overwritten.
+// TMEM: accumulator [0,192), A_hi [192,288), A_lo [288,384) — no room for a second operand buffer, so the loaders
+// refill the operand only after the tile's last MMA has retired (the next tile's observations are prefetched into the L2).
+// Values beyond the fp16 range (|x| > 65504) saturate.
+// =====================================================================================================
+constexpr int T3_COL_AH = 192, T3_COL_AL = 288;
+constexpr int T3_THREADS = TC_THREADS + 32;     // + the weight-streaming warp
+
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);            // exact differences
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+__global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTcParams Q) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    unsigned char *sW = tsm;                                             // 3 ring slots of TC_W_BYTES
+    float *sB = reinterpret_cast<float *>(sW + 3 * TC_W_BYTES);          // [3][192]
+    float *sW4 = sB + 3 * POL_HP;                                        // [A][192]
+    float *sb4 = sW4 + Q.base.A * POL_HP;                                // [A], padded to an even count
+    float *s_part = sb4 + ((Q.base.A + 1) & ~1);                         // [TC_M][A] partial outputs of the second column half
+    uint64_t *bar_mma = reinterpret_cast<uint64_t *>(s_part + TC_M * Q.base.A);   // a layer's MMAs retired
+    uint64_t *bar_afull = bar_mma + 1;                                   // loaders -> MMA thread: operand holds the tile's observations
+    uint64_t *bar_afree = bar_afull + 1;                                 // MMA thread -> loaders: the tile's last MMA retired
+    uint64_t *bar_full = bar_afree + 1;                                  // [3] weight chunk landed in slot
+    uint64_t *bar_free = bar_full + 3;                                   // [3] last MMA reading the slot retired
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_free + 3);
+    const PolicyParams &P = Q.base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int A = P.A, n_a = P.n_a;
+    const long my_tiles = (Q.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+    if (tid == 0) {
+        tc_mbar_init(bar_mma, 1); tc_mbar_init(bar_afull, TC_LOADERS * TC_M); tc_mbar_init(bar_afree, 1);
+        for (int k = 0; k < 3; ++k) { tc_mbar_init(&bar_full[k], 1); tc_mbar_init(&bar_free[k], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = tid; k < 3 * POL_HP + A * POL_HP + A; k += T3_THREADS) {
+        const float v = Q.small[k];
+        if (k < 3 * POL_HP) sB[k] = v;
+        else if (k < 3 * POL_HP + A * POL_HP) sW4[k - 3 * POL_HP] = v;
+        else sb4[k - 3 * POL_HP - A * POL_HP] = v;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"((uint32_t)TC_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int row = tid & (TC_M - 1);
+
+    if (warp == 4 * (TC_EPI + TC_LOADERS)) {
+        // ================= weight producer (one lane): chunk k of the endless sequence H1 L1 H2 L2 H3 L3 ... -> slot k % 3
+        if ((tid & 31) == 0) {
+            const long n_chunks = 6 * my_tiles;
+#pragma unroll 1
+            for (long k = 0; k < n_chunks; ++k) {
+                const int slot = (int)(k % 3);
+                if (k >= 3) tc_mbar_wait(&bar_free[slot], (uint32_t)((k / 3 - 1) & 1));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(&bar_full[slot])), "r"((uint32_t)TC_W_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(s_u32(sW + slot * TC_W_BYTES)), "l"(Q.w16 + (size_t)(k % 6) * TC_W_BYTES), "r"((uint32_t)TC_W_BYTES),
+                               "r"(s_u32(&bar_full[slot])) : "memory");
+            }
+        }
+    } else if (warp >= 4 * TC_EPI) {
+        // ================= loaders: observation row -> (hi, lo) fp16 -> operand A, after the previous tile's last MMA retired
+        int it = 0;
+#pragma unroll 1
+        for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x, ++it) {
+            if (tid == TC_CTHREADS) {                                    // pull the NEXT tile's observations into the L2
+                const long nt = tile + gridDim.x;
+                if (nt < Q.n_tiles) {
+                    const long e0 = nt * TC_M / n_a;
+                    long e1 = (nt * TC_M + TC_M - 1) / n_a; if (e1 * n_a >= P.n_cols) e1 = (P.n_cols - 1) / n_a;
+                    const size_t env_bytes = (size_t)P.K0 * n_a * sizeof(float);
+                    if ((env_bytes & 15) == 0)
+                        for (long ee = e0; ee <= e1; ++ee)
+                            for (size_t off = 0; off < env_bytes; off += 32768) {
+                                const uint32_t sz = (uint32_t)(env_bytes - off < 32768 ? env_bytes - off : 32768);
+                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char *>(P.obs) + ee * env_bytes + off), "r"(sz) : "memory");
+                            }
+                }
+            }
+            if (it >= 1) tc_mbar_wait(bar_afree, (uint32_t)(it - 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long col = tile * TC_M + row;
+            const bool valid = col < P.n_cols;
+            const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
+            const float *orow = P.obs + e * (long)P.K0 * n_a + ag;
+            constexpr int FPL = POL_HP / TC_LOADERS;
+            const int k_lo = ((warp - 4 * TC_EPI) >> 2) * FPL;
+#pragma unroll 1
+            for (int c = 0; c < FPL / 32; ++c) {
+                float f[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int k = k_lo + c * 32 + q;
+                    f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
+                }
+                uint32_t rh[16], rl[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) split_h2(f[2 * q], f[2 * q + 1], rh[q], rl[q]);
+                TC_ST16(lane_base + T3_COL_AH + (k_lo >> 1) + c * 16, rh);
+                TC_ST16(lane_base + T3_COL_AL + (k_lo >> 1) + c * 16, rl);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_mbar_arrive(bar_afull);
+        }
+    } else {
+        // ================= compute: thread 0 issues the MMAs; two warps per lane quadrant share a row's epilogue
+        const int half = warp >> 2;
+        uint32_t par_mma = 0;
+        long kc = 0;                                                     // weight-chunk counter (thread 0)
+        int it = 0;
+#pragma unroll 1
+        for (long tile = blockIdx.x; tile < Q.n_tiles; tile += gridDim.x, ++it) {
+            const long col = tile * TC_M + row;
+            const bool valid = col < P.n_cols;
+            const long e = valid ? col / n_a : 0; const int ag = valid ? (int)(col - e * n_a) : 0;
+            float out[TC_AMAX];
+#pragma unroll
+            for (int j = 0; j < TC_AMAX; ++j) out[j] = 0.f;
+#pragma unroll 1
+            for (int layer = 0; layer < 3; ++layer) {
+                if (layer > 0) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory");
+                }
+                if (tid == 0) {
+                    if (layer == 0) tc_mbar_wait(bar_afull, (uint32_t)it & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int g = 0; g < 3; ++g) {                        // (A_hi, H), (A_lo, H), (A_hi, L)
+                        const long kk = kc + (g == 2 ? 1 : 0);
+                        const int slot = (int)(kk % 3);
+                        if (g != 1) { tc_mbar_wait(&bar_full[slot], (uint32_t)((kk / 3) & 1)); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                        const uint32_t wbase = s_u32(sW + slot * TC_W_BYTES);
+                        const uint32_t acol = (g == 1) ? T3_COL_AL : T3_COL_AH;
+#pragma unroll 1
+                        for (int j = 0; j < POL_HP / 16; ++j) {
+                            const uint64_t bdesc = tc_smem_desc(wbase + (uint32_t)j * 2u * TC_LBO);
+                            const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                                ::"r"(tmem + TC_COL_D), "r"(tmem + acol + j * 8), "l"(bdesc), "r"(TC_IDESC), "r"(acc), "r"(0u) : "memory");
+                        }
+                        if (g >= 1) tc_commit(&bar_free[slot]);          // H after its second use, L after its only use
+                    }
+                    kc += 2;
+                    tc_commit(bar_mma);
+                    if (layer == 2) tc_commit(bar_afree);
+                }
+                tc_mbar_wait(bar_mma, par_mma); par_mma ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const float *bias = sB + layer * POL_HP;
+#pragma unroll 1
+                for (int c = half * (POL_HP / 32 / TC_EPI); c < (half + 1) * (POL_HP / 32 / TC_EPI); ++c) {
+                    uint32_t v[32];
+                    TC_LD32(lane_base + TC_COL_D + c * 32, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (Q.debug && layer == 0 && valid) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) Q.debug[col * POL_HP + c * 32 + q] = __uint_as_float(v[q]);
+                    }
+                    float h[32];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 b4v = *reinterpret_cast<const float4 *>(bias + c * 32 + q4 * 4);
+                        const float bb[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float s_ = __uint_as_float(v[q4 * 4 + u]) + bb[u];
+                            h[q4 * 4 + u] = s_ > 0.f ? s_ : s_ * P.slope;
+                        }
+                    }
+                    if (layer < 2) {
+                        uint32_t rh[16], rl[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) split_h2(h[2 * q], h[2 * q + 1], rh[q], rl[q]);
+                        TC_ST16(lane_base + T3_COL_AH + c * 16, rh);
+                        TC_ST16(lane_base + T3_COL_AL + c * 16, rl);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TC_AMAX; ++j) {
+                            if (j < A) {
+                                float s_ = out[j];
+#pragma unroll
+                                for (int q4 = 0; q4 < 8; ++q4) {
+                                    const float4 w = *reinterpret_cast<const float4 *>(sW4 + j * POL_HP + c * 32 + q4 * 4);
+                                    s_ = fmaf(h[q4 * 4], w.x, s_); s_ = fmaf(h[q4 * 4 + 1], w.y, s_);
+                                    s_ = fmaf(h[q4 * 4 + 2], w.z, s_); s_ = fmaf(h[q4 * 4 + 3], w.w, s_);
+                                }
+                                out[j] = s_;
+                            }
+                        }
+                    }
+                }
+                if (layer < 2) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            if (half == 1) {
+#pragma unroll
+                for (int j = 0; j < TC_AMAX; ++j) if (j < A) s_part[row * A + j] = out[j];
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_CTHREADS) : "memory");
+            if (valid && half == 0) {
+                float q2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < TC_AMAX; ++j) {
+                    if (j >= A) break;
+                    float a = tanhf((out[j] + s_part[row * A + j]) + sb4[j]);
+                    if (P.explore == 1) {
+                        const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                        const float u1 = ((float)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);
+                        const float u2 = (float)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
+                        const float g = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+                        q2 += g * g;
+                        a = fminf(fmaxf(a + g * P.scale, -1.f), 1.f);
+                    } else if (P.explore == 2) {
+                        const uint64_t r = pol_mix64(P.seed, P.step, (uint64_t)col, (uint64_t)j);
+                        a = (float)(r >> 40) * (2.0f / 16777216.0f) - 1.0f;
+                    }
+                    P.act[(e * A + j) * n_a + ag] = a;
+                }
+                if (P.log_pi) {
+                    float lp = 0.f;
+                    if (P.explore == 2) lp = -(float)A * 0.69314718056f;
+                    else if (P.explore == 1) lp = -0.5f * q2 - (float)A * logf(P.scale * 2.50662827463f);
+                    P.log_pi[e * n_a + ag] = lp;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_COLS) : "memory");
+}
+
 }  // namespace swarm

@@ -34,8 +34,9 @@ class DevicePolicy:
 
     def set_precision(self, precision):
         """'fp32': exact path (FFMA, agrees with torch fp32 to rounding).  'f16_tc': persistent tcgen05 kernel, fp16 operands
-        with fp32 accumulation in tensor memory (fast mode, ~1e-3 absolute deviation on the tanh output)."""
-        mode = {"fp32": _lib.SWARM_POLICY_FP32, "f16_tc": _lib.SWARM_POLICY_F16_TC}[precision]
+        with fp32 accumulation in tensor memory (fast mode, ~1e-3 absolute deviation on the tanh output).  'f16x3_tc': the same
+        kernel structure with every operand split into fp16 hi + lo (three MMAs per k-step): fp32-accurate (~1e-6)."""
+        mode = {"fp32": _lib.SWARM_POLICY_FP32, "f16_tc": _lib.SWARM_POLICY_F16_TC, "f16x3_tc": _lib.SWARM_POLICY_F16X3_TC}[precision]
         check(self.lib.swarm_policy_set_precision(self._h, mode), "swarm_policy_set_precision")
         self.precision = precision
 

@@ -110,3 +110,31 @@ def test_tensor_core_policy_layer1_and_outputs(E, n_a):
     pol.set_precision("fp32")
     act32, _ = pol.step(obs.cuda())
     torch.testing.assert_close(act32.cpu(), exact, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("E,n_a", [(64, 30), (5, 7), (1, 1), (3, 1024), (700, 30)])
+def test_split_fp16_tensor_core_policy_is_fp32_accurate(E, n_a):
+    """'f16x3_tc': operands split into fp16 hi + lo, three tcgen05.mma per k-step, weights streamed through a 3-slot ring
+    (700 x 30 agents = 165 tiles > 148 SMs: CTAs loop, the ring wraps).  Same tolerance as the exact FFMA path."""
+    D, H, A = 192, 180, 2
+    torch.manual_seed(23 + n_a)
+    ref = RefMLP(D, A, H)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.mul_(3.0)
+    obs = torch.randn(E, D, n_a) * 0.7
+    obs[:, 32:, :] *= (torch.rand(E, D - 32, n_a) < 0.2)
+    pol = DevicePolicy(D, A, H, precision="f16x3_tc").load_state_dict(ref.state_dict())
+    dbg = torch.full((E * n_a, 192), float("nan"), device="cuda")
+    pol.lib.swarm_policy_debug_buffer(pol._h, dbg.data_ptr())
+    act, _ = pol.step(obs.cuda())
+    pol.lib.swarm_policy_debug_buffer(pol._h, None)
+    x = obs.permute(0, 2, 1).reshape(E * n_a, D)
+    with torch.no_grad():
+        want1 = (x.double() @ ref.fc1.weight.double().t()).float()
+        exact = ref(x).reshape(E, n_a, A).permute(0, 2, 1)
+    torch.testing.assert_close(dbg.cpu()[:, :H], want1, rtol=2e-6, atol=2e-5)
+    # the dropped lo x lo products are 2^-22 relative per term: with pre-activations of O(10) that is a few 1e-6 absolute
+    torch.testing.assert_close(act.cpu(), exact, rtol=1e-5, atol=1e-5)   # 1e-5 of the (-1, 1) action range; observed max 6e-6
+    act2, _ = pol.step(obs.cuda())
+    assert torch.equal(act, act2)                               # deterministic

@@ -33,5 +33,5 @@ t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
 print(f"host time per call {(t1 - t0) / 5 * 1e3:.3f} ms, total per call incl. drain {(t2 - t0) / 5 * 1e3:.3f} ms", file=sys.stderr)
 flop = 2.0 * E * n_a * (D * H + H * H * 2 + H * A)
 flop_padded = 2.0 * E * n_a * (192 * 192 * 3 + 192 * A)
-print(json.dumps({"kernel": "k_policy_mlp" + ("_tc" if prec == "f16_tc" else ""), "agents": E * n_a, "ms": ms, "agent_forwards_per_s": E * n_a / ms * 1e3,
+print(json.dumps({"kernel": "k_policy_mlp" + ("_tc" if prec == "f16_tc" else "_tc3" if prec == "f16x3_tc" else ""), "agents": E * n_a, "ms": ms, "agent_forwards_per_s": E * n_a / ms * 1e3,
                   "useful_TFLOPs": flop / ms / 1e9, "issued_TFLOPs": flop_padded / ms / 1e9}))
