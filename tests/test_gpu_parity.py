@@ -471,3 +471,48 @@ def test_two_launch_step_equals_fused_step(monkeypatch):
         assert torch.equal(sims[0][0].sensed_index, sims[1][0].sensed_index) and torch.equal(sims[0][0].occupied_index, sims[1][0].occupied_index)
         assert np.array_equal(sims[0][0].obs.cpu().numpy(), ob.obs), t
     assert sims[0][0].launch_count - l0[0][0] == 100 and sims[1][0].launch_count - l0[1][0] == 50
+
+
+def test_config3_full_size_65536_envs_properties():
+    """BASELINE config 3 at its full size (65 536 envs x 30 agents, production layout), checked through properties that do
+    not need 65 536 oracle envs: (1) 128 sampled envs follow the oracle bit for bit at every step (an env's result does not
+    depend on its neighbours in the batch); (2) the same batch stepped by a second simulator gives identical tensors
+    (determinism: checksum of every output); (3) observe() is idempotent; (4) done stays False, rewards are 0/1."""
+    import bench
+    E, n_a, steps = 65536, 30, 25
+    shapes = load_shapes()
+    ngm = int(shapes["n_g"].max())
+    r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    blocks, n_g, l_cell, p, dp = bench.synth_batch(E, n_a, shapes, 7, "random")
+    sims = [make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32) for _ in range(2)]
+    for s_ in sims:
+        s_.set_grid(blocks, n_g, l_cell); s_.set_state(p, dp); s_.observe()
+    pick = np.random.RandomState(0).choice(E, 128, replace=False)
+    params = [orc.make_params(n_a, int(n_g[e]), float(l_cell[e]), r_avoid) for e in pick]
+    ob = orc.OracleBatch(params, nthreads=16)
+    for k, e in enumerate(pick):
+        ob.set_grid(k, blocks[e, :2 * n_g[e]].reshape(2, n_g[e]))
+    ob.p[:], ob.dp[:] = p[pick], dp[pick]
+    ob.observe()
+    tp = torch.from_numpy(pick).cuda()
+    assert np.array_equal(sims[0].obs[tp].cpu().numpy(), ob.obs.astype(np.float32))
+    o0 = sims[0].obs.clone(); sims[0].observe(); assert torch.equal(o0, sims[0].obs)          # idempotent
+    act = torch.empty(E, 2, n_a, dtype=torch.float32, device="cuda")
+    for t in range(steps):
+        sims[0].fill_actions(act, seed=11, step=t)
+        a = act[tp].cpu().numpy()
+        if t % 2:                                                   # drive the sampled envs (and only them) into their shapes
+            a = goal_seeking_action(ob.obs, ob.dp, np.random.RandomState(t), noise=0.1)
+            act[tp] = torch.from_numpy(a).cuda()
+        for s_ in sims:
+            s_.step(act)
+        ob.step(a)
+        assert np.array_equal(sims[0].p[tp].cpu().numpy(), ob.p) and np.array_equal(sims[0].dp[tp].cpu().numpy(), ob.dp), t
+        assert np.array_equal(sims[0].obs[tp].cpu().numpy(), ob.obs.astype(np.float32)), t
+        assert np.array_equal(sims[0].reward[tp].cpu().numpy(), ob.reward.astype(np.float32)), t
+        assert np.array_equal(sims[0].a_prior[tp].cpu().numpy(), ob.a_prior.astype(np.float32)), t
+        assert np.array_equal(sims[0].neighbor_index[tp].cpu().numpy(), ob.neighbor_index), t
+    for name in ("p", "dp", "obs", "reward", "a_prior", "neighbor_index", "in_flags", "nearest_cell"):
+        assert torch.equal(getattr(sims[0], name), getattr(sims[1], name)), name
+    assert not sims[0].done.any() and bool(((sims[0].reward == 0) | (sims[0].reward == 1)).all())
+    assert torch.isfinite(sims[0].obs).all() and torch.isfinite(sims[0].p).all()
