@@ -35,7 +35,7 @@ class BatchedAssemblySim:
     def __init__(self, num_envs, n_a, n_g_max, r_avoid, *, device=0, out_dtype=torch.float32, emit_indices=False,
                  want_prior=True, is_con_self_state=True, is_periodic=False, d_sen=0.4, size_a=0.035, k_ball=30.0,
                  k_wall=100.0, c_wall=5.0, dt=0.1, vel_max=0.8, mass=1.0, half_width=2.4, half_height=2.4,
-                 exact_occupancy=False, brute_force_scan=False):
+                 exact_occupancy=False, brute_force_scan=False, guard_bytes=0):
         if not torch.cuda.is_available():
             raise SwarmError("BatchedAssemblySim needs a CUDA device; there is no CPU fallback")
         if out_dtype not in (torch.float32, torch.float64):
@@ -66,7 +66,20 @@ class BatchedAssemblySim:
         self.n_g_pad = int(self.lib.swarm_grid_pad(self.n_g_max))
 
         E, n, dev = self.E, self.n_a, self.device
-        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)   # noqa: E731
+        # guard_bytes > 0 (tests): every device buffer sits between two guard zones filled with 0xA5; check_guards() verifies
+        # that no kernel wrote outside its arrays (compute-sanitizer is not available on the GPU pool)
+        self._guards = []
+        gb = (int(guard_bytes) + 255) // 256 * 256
+
+        def z(*shape, dtype):
+            if not gb:
+                return torch.zeros(*shape, dtype=dtype, device=dev)
+            numel = int(np.prod(shape)) if shape else 1
+            nbytes = (numel * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256
+            raw = torch.full((gb + nbytes + gb,), 0xA5, dtype=torch.uint8, device=dev)
+            raw[gb:gb + nbytes] = 0
+            self._guards.append((raw, gb, nbytes))
+            return raw[gb:gb + numel * torch.empty((), dtype=dtype).element_size()].view(dtype).view(*shape)
         self.p = z(E, 2, n, dtype=torch.float64)
         self.dp = z(E, 2, n, dtype=torch.float64)
         self._grid = z(E, self.n_g_pad, 2, dtype=torch.float64)
@@ -79,11 +92,11 @@ class BatchedAssemblySim:
         self.reward = z(E, 1, n, dtype=out_dtype)
         self.done = z(E, 1, n, dtype=torch.bool)
         self._a_prior = [z(E, 2, n, dtype=out_dtype), z(E, 2, n, dtype=out_dtype)]
-        self.neighbor_index = torch.full((E, n, TOPO_NEI_MAX), -1, dtype=torch.int32, device=dev)
+        self.neighbor_index = z(E, n, TOPO_NEI_MAX, dtype=torch.int32).fill_(-1)
         self.in_flags = z(E, n, dtype=torch.int32)
         if emit_indices:
-            self.sensed_index = torch.full((E, n, NUM_OBS_GRID_MAX), -1, dtype=torch.int32, device=dev)
-            self.occupied_index = torch.full((E, n, NUM_OCC_GRID_MAX), -1, dtype=torch.int32, device=dev)
+            self.sensed_index = z(E, n, NUM_OBS_GRID_MAX, dtype=torch.int32).fill_(-1)
+            self.occupied_index = z(E, n, NUM_OCC_GRID_MAX, dtype=torch.int32).fill_(-1)
         else:
             self.sensed_index = self.occupied_index = None
 
@@ -196,6 +209,14 @@ class BatchedAssemblySim:
         assert obs.is_cuda and obs.is_contiguous() and obs.shape == self.obs.shape and obs.dtype == self.obs.dtype
         check(self.lib.swarm_set_obs_buffer(self._h, C.c_void_p(obs.data_ptr())), "swarm_set_obs_buffer")
         self.obs = obs
+
+    def check_guards(self):
+        """True iff every guard zone around the device buffers still holds its fill pattern (needs guard_bytes > 0)."""
+        assert self._guards, "construct with guard_bytes > 0"
+        ok = True
+        for raw, gb, nbytes in self._guards:
+            ok = ok and bool((raw[:gb] == 0xA5).all()) and bool((raw[gb + nbytes:] == 0xA5).all())
+        return ok
 
     def mark_state_dirty(self):
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")

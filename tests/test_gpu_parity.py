@@ -516,3 +516,28 @@ def test_config3_full_size_65536_envs_properties():
         assert torch.equal(getattr(sims[0], name), getattr(sims[1], name)), name
     assert not sims[0].done.any() and bool(((sims[0].reward == 0) | (sims[0].reward == 1)).all())
     assert torch.isfinite(sims[0].obs).all() and torch.isfinite(sims[0].p).all()
+
+
+@pytest.mark.parametrize("n_a,E,emit,dt", [(30, 61, True, torch.float64), (30, 61, False, torch.float32), (7, 33, True, torch.float64),
+                                           (100, 9, True, torch.float64), (1, 5, False, torch.float32)])
+def test_no_kernel_writes_outside_its_buffers(n_a, E, emit, dt):
+    """Every device buffer of the simulator is allocated between two 64 KB guard zones (compute-sanitizer is closed on this
+    GPU pool); after set_grid / reset / observe / steps through every emission path the guards must be untouched."""
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=900 + n_a)
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit, guard_bytes=65536)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe()
+    rng = np.random.RandomState(4)
+    for t in range(40):
+        a = goal_seeking_action(ob.obs, ob.dp, rng) if t % 3 else rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+    assert np.array_equal(sim.p.cpu().numpy(), ob.p)
+    sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+    sim.reset(seed=5); sim.metrics()
+    act = torch.empty(E, 2, n_a, dtype=torch.float32, device="cuda")
+    for t in range(5):
+        sim.step(sim.fill_actions(act, seed=1, step=t))
+    torch.cuda.synchronize()
+    assert sim.check_guards()
