@@ -199,6 +199,10 @@ void *swarm_a_prior_ptr(swarm_sim *sim);
  * bit-identical to oracle/assembly_oracle.c:orc_fill_actions.  Benchmark / test input only. */
 int swarm_fill_actions(swarm_sim *sim, uint64_t seed, uint64_t step, uint64_t env_offset, float *act_dev, void *stream);
 
+/* Test hook: psi = _rho_cos_dec(z, delta = 0, r) (CPP:1012-1020) of n HOST values through the device implementation
+ * (the kernels use their own [0, pi] cosine instead of libdevice's). */
+int swarm_debug_rho(const double *z_host, int32_t n, double r, double *out_host);
+
 /* number of kernels this handle has launched so far */
 int64_t swarm_launch_count(const swarm_sim *sim);
 /* dynamic shared memory bytes and threads per CTA of the fused step kernel for this handle */

@@ -42,7 +42,7 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer",
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
-                   "swarm_abi_version", "swarm_sqrt_threshold"]
+                   "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho"]
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
                   "swarm_policy_set_precision", "swarm_policy_debug_buffer"]
@@ -106,6 +106,7 @@ def load():
     lib.swarm_policy_debug_buffer.argtypes = [C.c_void_p, C.c_void_p]
     lib.swarm_policy_launch_count.restype = C.c_int64
     lib.swarm_policy_launch_count.argtypes = [C.c_void_p]
+    lib.swarm_debug_rho.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
     lib.swarm_sqrt_threshold.restype = C.c_double
     lib.swarm_sqrt_threshold.argtypes = [C.c_double, C.c_int]
     _lib = lib

@@ -412,6 +412,19 @@ int swarm_fill_actions(swarm_sim *s, uint64_t seed, uint64_t step, uint64_t env_
     return SWARM_OK;
 }
 
+/* test hook: psi = _rho_cos_dec(z, 0, r) (CPP:1012-1020) of n HOST values through the device implementation */
+int swarm_debug_rho(const double *z_host, int32_t n, double r, double *out_host) {
+    if (!z_host || !out_host || n <= 0) return fail(SWARM_ERR_INVALID, "bad argument");
+    double *d = nullptr;
+    CU_TRY(cudaMalloc(&d, sizeof(double) * 2 * (size_t)n));
+    cudaError_t e = cudaMemcpy(d, z_host, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { k_debug_rho<<<(n + 255) / 256, 256>>>(d, n, r, d + n); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpy(out_host, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SWARM_ERR_CUDA, std::string("swarm_debug_rho: ") + cudaGetErrorString(e));
+    return SWARM_OK;
+}
+
 int64_t swarm_launch_count(const swarm_sim *s) { return s ? s->launches : 0; }
 
 int swarm_kernel_geometry(const swarm_sim *s, int32_t *threads_per_cta, int32_t *smem_bytes, int32_t *ctas) {
