@@ -172,6 +172,16 @@ int swarm_reset(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_of
  * {coverage_rate, distribution_uniformity, voronoi_based_uniformity} (assembly_wrapper.py:48-72, 74-101, 103-129). */
 int swarm_metrics(swarm_sim *sim, double *out_dev, void *stream);
 
+/* The reference env's own action strategies (ENV:519-601, Python/NumPy there) for the CURRENT state of every env:
+ * SWARM_STRATEGY_RULE = agent_strategy 'rule' (ENV:530-601, the expert controller of collect_expert_data.py),
+ * SWARM_STRATEGY_LLM = 'llm' (ENV:524-529 -> robot_prior_policy ENV:876-941; uses the neighbour list of the last
+ * observation).  act_dev: DEVICE [E][2][n_a] f64, to be passed to swarm_step with SWARM_F64 (ENV:633 u = a).
+ * Arithmetic: plain IEEE binary64 in the reference's evaluation order; the NumPy original itself varies in the last
+ * bits with the NumPy / BLAS build (np.linalg.norm -> BLAS dot, pairwise np.sum), agreement is ~1e-15. */
+#define SWARM_STRATEGY_RULE 1
+#define SWARM_STRATEGY_LLM 2
+int swarm_strategy_actions(swarm_sim *sim, int kind, double *act_dev, void *stream);
+
 /* Redirect the observation output of the following observe / step calls to another device buffer of the same shape and
  * dtype.  Lets a device-resident rollout loop keep the previous observation (policy input, replay `obs`) and the new one
  * (replay `next_obs`) without a copy: alternate two buffers. */

@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(PKG, "lib", "libswar
 
 SWARM_OK, SWARM_ERR_INVALID, SWARM_ERR_UNSUPPORTED, SWARM_ERR_CUDA, SWARM_ERR_NO_DEVICE = range(5)
 SWARM_F64, SWARM_F32 = 0, 1
+SWARM_STRATEGY_RULE, SWARM_STRATEGY_LLM = 1, 2
 
 
 class SwarmConfig(C.Structure):
@@ -39,7 +40,7 @@ class SwarmBuffers(C.Structure):
 # every symbol include/swarm_b200.h declares (tests check the library exports all of them)
 LEGACY_SYMBOLS = ["_get_observation", "_get_reward", "_sf_b2b_all", "_get_dist_b2w", "calculateActionPrior"]
 BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_destroy", "swarm_set_grid",
-                   "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer",
+                   "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer", "swarm_strategy_actions",
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho"]
@@ -83,6 +84,7 @@ def load():
     lib.swarm_set_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_mark_state_dirty.argtypes = [C.c_void_p]
     lib.swarm_set_obs_buffer.argtypes = [C.c_void_p, C.c_void_p]
+    lib.swarm_strategy_actions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.swarm_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_set_shapes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_reset.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]

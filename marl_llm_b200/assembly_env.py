@@ -65,9 +65,10 @@ class AssemblySwarmEnv:
         self.alpha = 1
         if self.dynamics_mode != "Cartesian":
             raise NotImplementedError("only dynamics_mode='Cartesian' exists in the reference (ENV:141-146)")
-        if self.agent_strategy != "input":
-            raise NotImplementedError("agent_strategy 'random'/'rule'/'llm' run on the host in the reference (ENV:523-601); "
-                                      "only 'input' is on the GPU path")
+        if self.agent_strategy not in ("input", "random", "rule", "llm"):
+            raise ValueError("Wrong in Step function")                   # ENV:602-603
+        if self.agent_strategy in ("rule", "llm") and self.is_periodic:
+            raise NotImplementedError("the 'rule' / 'llm' strategies are implemented for is_boundary=True")
         self.results_file = args.results_file
         if isinstance(self.results_file, dict):
             loaded = self.results_file
@@ -226,10 +227,18 @@ class AssemblySwarmEnv:
         self.simulation_time += self.dt
         if self._grid_dirty:
             self._push_grid()
-        a = np.ascontiguousarray(a)
-        if a.dtype not in (np.float32, np.float64):
-            a = a.astype(np.float64)
-        act = torch.from_numpy(a).reshape(self.num_envs, 2, self.n_a).to(self._sim.device)
+        # ENV:519-601: 'input' uses the caller's action; 'random' draws it from NumPy's global stream like the reference;
+        # 'rule' / 'llm' are evaluated on the device from the pre-step state (swarm_strategy_actions)
+        if self.agent_strategy == "random":
+            a = np.random.uniform(-1, 1, (self.num_envs, 2, self.n_a) if self.num_envs > 1 else (2, self.n_a))   # ENV:522-523
+        if self.agent_strategy in ("rule", "llm"):
+            act = self._sim.strategy_actions(self.agent_strategy)
+            a = act.cpu().numpy().reshape((self.num_envs, 2, self.n_a) if self.num_envs > 1 else (2, self.n_a))
+        else:
+            a = np.ascontiguousarray(a)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            act = torch.from_numpy(a).reshape(self.num_envs, 2, self.n_a).to(self._sim.device)
         obs, rew, done, _, prior = self._sim.step(act)
         info = np.array([None, None, None]).reshape(3, 1)               # ENV:484-485
         u = a.astype(np.float64)

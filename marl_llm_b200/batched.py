@@ -203,6 +203,16 @@ class BatchedAssemblySim:
         self.dp.copy_(torch.as_tensor(dp, dtype=torch.float64).reshape(self.E, 2, self.n_a))
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
 
+    def strategy_actions(self, kind, out=None):
+        """Actions of the reference env's own strategies for the current state: kind 'rule' (assembly.py:530-601) or 'llm'
+        (assembly.py:524-529, 876-941).  [E, 2, n_a] float64 CUDA tensor; pass it to step() (float64 actions, assembly.py:633)."""
+        k = {"rule": _lib.SWARM_STRATEGY_RULE, "llm": _lib.SWARM_STRATEGY_LLM}[kind]
+        if out is None:
+            out = torch.empty(self.E, 2, self.n_a, dtype=torch.float64, device=self.device)
+        assert out.is_cuda and out.dtype == torch.float64 and out.is_contiguous() and out.numel() == self.E * 2 * self.n_a
+        check(self.lib.swarm_strategy_actions(self._h, k, C.c_void_p(out.data_ptr()), self._stream()), "swarm_strategy_actions")
+        return out
+
     def set_obs_buffer(self, obs):
         """Redirect the observation output of the following observe()/step() calls to `obs` (same shape / dtype, CUDA,
         contiguous); `self.obs` then refers to it.  Alternate two buffers to keep the previous observation without a copy."""

@@ -311,6 +311,24 @@ int swarm_metrics(swarm_sim *s, double *out_dev, void *stream) {
     return SWARM_OK;
 }
 
+int swarm_strategy_actions(swarm_sim *s, int kind, double *act_dev, void *stream) {
+    if (!s || !act_dev) return fail(SWARM_ERR_INVALID, "null argument");
+    if (kind != SWARM_STRATEGY_RULE && kind != SWARM_STRATEGY_LLM) return fail(SWARM_ERR_INVALID, "kind must be SWARM_STRATEGY_RULE or SWARM_STRATEGY_LLM");
+    if (kind == SWARM_STRATEGY_LLM && !s->observed) return fail(SWARM_ERR_INVALID, "the 'llm' strategy needs the neighbour list of an observation");
+    if (s->cfg.is_periodic) return fail(SWARM_ERR_UNSUPPORTED, "strategies are implemented for is_boundary=True (the reference's Python twins never wrap)");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const int n_a = s->cfg.n_a, th = n_a < 256 ? round32(n_a) : 256;
+    if (kind == SWARM_STRATEGY_RULE)
+        k_strategy<1><<<s->cfg.num_envs, th, 0, (cudaStream_t)stream>>>(n_a, TOPO, s->K.p, s->K.dp, s->K.grid, s->K.n_g_pad, s->K.n_g, s->K.in_thresh,
+                                                                      s->K.nbr, s->K.d_sen, s->K.r_avoid, s->K.n_obs_max, act_dev);
+    else
+        k_strategy<2><<<s->cfg.num_envs, th, 0, (cudaStream_t)stream>>>(n_a, TOPO, s->K.p, s->K.dp, s->K.grid, s->K.n_g_pad, s->K.n_g, s->K.in_thresh,
+                                                                      s->K.nbr, s->K.d_sen, s->K.r_avoid, s->K.n_obs_max, act_dev);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    return SWARM_OK;
+}
+
 int swarm_set_obs_buffer(swarm_sim *s, void *obs_dev) {
     if (!s || !obs_dev) return fail(SWARM_ERR_INVALID, "null argument");
     s->buf.obs = obs_dev; s->K.obs = obs_dev;

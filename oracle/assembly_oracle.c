@@ -477,4 +477,141 @@ void orc_fill_actions(int E, int n_a, uint64_t seed, uint64_t step, uint64_t env
         }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side action strategies of the reference env (ENV:519-601, Python/NumPy in the reference):
+ *   'rule' (ENV:530-601, the expert controller of collect_expert_data.py) and 'llm' (ENV:524-529 ->
+ *   robot_prior_policy ENV:876-941, the Python twin of CPP:1121-1196 with repulsion_strength = 1.0).
+ * Restated with plain IEEE binary64, every operation individually rounded, sums in index order.
+ * NOT bit-identical to the NumPy original and cannot be made so portably: np.linalg.norm of a 1-D
+ * vector goes through the BLAS dot (FMA on x86-64), np.sum uses pairwise/unrolled summation and
+ * np.cos NumPy's own SIMD kernels — all of which vary with the NumPy/BLAS build.  Measured here
+ * (NumPy 2.3.5 + OpenBLAS): <= 2e-15 absolute on the actions; tests/test_oracle_vs_reference.py
+ * pins the restatement at 1e-12 per step.  The CUDA kernel (k_strategy) follows THIS file bit for bit.
+ * ------------------------------------------------------------------------------------------ */
+static int round_half_even(double x) {            /* np.round, ENV:565 */
+    double f = floor(x), d = x - f;
+    if (d > 0.5) return (int)f + 1;
+    if (d < 0.5) return (int)f;
+    return ((long long)f % 2 == 0) ? (int)f : (int)f + 1;
+}
+
+void orc_rule_actions(const orc_params *P, const double *p, const double *dp, const double *grid, double *a /* [2][n_a] */) {
+    const int n = P->n_a, ng = P->n_g, NO = P->num_obs_grid_max;
+    const double k_1 = 1, k_2 = 15, k_3 = 17;                                 /* ENV:532 */
+    int *sensed = (int *)malloc(sizeof(int) * ng), *keep = (int *)malloc(sizeof(int) * ng), *fin = (int *)malloc(sizeof(int) * (NO > ng ? NO : ng));
+    for (int i = 0; i < n; ++i) {
+        const double x = p[i], y = p[n + i], vx = dp[i], vy = dp[n + i];
+        /* _get_trgt_grid_state, ENV:828-844 */
+        int min_index = 0, ns = 0; double min_dist = INFINITY;
+        for (int c = 0; c < ng; ++c) {
+            const double rx = grid[c] - x, ry = grid[ng + c] - y;
+            const double d = sqrt(rx * rx + ry * ry);                        /* np.linalg.norm(axis=0) */
+            if (d < min_dist) { min_dist = d; min_index = c; }               /* np.argmin: first minimum */
+            if (d < P->d_sen) sensed[ns++] = c;                              /* ENV:842 */
+        }
+        const int in_flag = min_dist < sqrt(2.0) * P->l_cell / 2;            /* ENV:832 */
+        const double tpx = in_flag ? x : grid[min_index], tpy = in_flag ? y : grid[ng + min_index];
+        const double tvx = in_flag ? vx : 0.0, tvy = in_flag ? vy : 0.0;
+        const double relx = tpx - x, rely = tpy - y, velx = tvx - vx, vely = tvy - vy;   /* ENV:536-537 */
+        double entx = 0.0, enty = 0.0;
+        if (!in_flag) {                                                      /* ENV:541 */
+            const double nr = sqrt(relx * relx + rely * rely) + 1e-8;
+            entx = k_1 * (relx / nr) + velx; enty = k_1 * (rely / nr) + vely;
+        }
+        /* exploration velocity, ENV:543-589 */
+        if (ns > 0 && in_flag) {                                             /* ENV:547-558: drop the occupied cells */
+            for (int j = 0; j < n; ++j) {
+                const double ax = p[j] - x, ay = p[n + j] - y;
+                if (!(sqrt(ax * ax + ay * ay) < P->d_sen + P->r_avoid / 2)) continue;    /* nearby agents, self included */
+                int m = 0;
+                for (int u = 0; u < ns; ++u) {
+                    const int c = sensed[u];
+                    const double gx = grid[c] - p[j], gy = grid[ng + c] - p[n + j];
+                    if (sqrt(gx * gx + gy * gy) > P->r_avoid / 2) keep[m++] = c;
+                }
+                memcpy(sensed, keep, sizeof(int) * m); ns = m;
+            }
+        }
+        int nf = 0;
+        if (ns > NO) {                                                       /* ENV:562-567 */
+            const double step = (double)(ns - 1) / (double)(NO - 1);
+            for (int t = 0; t < NO; ++t) fin[t] = sensed[round_half_even((double)t * step)];
+            nf = NO;
+        } else { memcpy(fin, sensed, sizeof(int) * ns); nf = ns; }
+        double expx = 0.0, expy = 0.0;
+        if (nf > 0) {                                                        /* ENV:575-586 */
+            double num0 = 0.0, num1 = 0.0, den = 0.0;
+            for (int u = 0; u < nf; ++u) {
+                const double gx = grid[fin[u]] - x, gy = grid[ng + fin[u]] - y;
+                const double z = sqrt(gx * gx + gy * gy);
+                const double psi = rho_cos_dec(z, 0.0, P->d_sen);            /* ENV:866-869 */
+                num0 += psi * gx; num1 += psi * gy; den += psi;
+            }
+            if (den == 0) den = 1e-8;
+            expx = k_2 * num0 / den; expy = k_2 * num1 / den;
+        }
+        /* interaction velocity, ENV:588-599: ALL agents within d_sen, not the top-6 list */
+        int nn = 0;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            const double ax = p[j] - x, ay = p[n + j] - y;
+            if (sqrt(ax * ax + ay * ay) < P->d_sen) ++nn;
+        }
+        double intx = 0.0, inty = 0.0;
+        for (int j = 0; j < n && nn > 0; ++j) {
+            if (j == i) continue;
+            const double ax = p[j] - x, ay = p[n + j] - y;
+            const double d = sqrt(ax * ax + ay * ay);
+            if (!(d < P->d_sen)) continue;
+            if (d < P->r_avoid) {
+                const double f = -k_3 * (P->r_avoid / d - 1);
+                intx += f * ax; inty += f * ay;
+            }
+            intx += 5 * (dp[j] - vx) / nn; inty += 5 * (dp[n + j] - vy) / nn;
+        }
+        const double sx = entx + expx + intx, sy = enty + expy + inty;       /* ENV:600 */
+        a[i] = sx < -1 ? -1 : (sx > 1 ? 1 : sx);                             /* np.clip, ENV:601 */
+        a[n + i] = sy < -1 ? -1 : (sy > 1 ? 1 : sy);
+    }
+    free(sensed); free(keep); free(fin);
+}
+
+/* 'llm' strategy: ENV:524-529 -> robot_prior_policy (ENV:876-941) with the target of _get_trgt_grid_state. */
+void orc_llm_actions(const orc_params *P, const double *p, const double *dp, const double *grid,
+                     const int32_t *neighbor_index, double *a /* [2][n_a] */) {
+    const int n = P->n_a, ng = P->n_g, K = P->topo_nei_max;
+    for (int i = 0; i < n; ++i) {
+        const double x = p[i], y = p[n + i], vx = dp[i], vy = dp[n + i];
+        int min_index = 0; double min_dist = INFINITY;
+        for (int c = 0; c < ng; ++c) {
+            const double rx = grid[c] - x, ry = grid[ng + c] - y;
+            const double d = sqrt(rx * rx + ry * ry);
+            if (d < min_dist) { min_dist = d; min_index = c; }
+        }
+        const int in_flag = min_dist < sqrt(2.0) * P->l_cell / 2;
+        const double dirx = (in_flag ? x : grid[min_index]) - x, diry = (in_flag ? y : grid[ng + min_index]) - y;
+        double fx = 0.0, fy = 0.0;
+        const double dist = sqrt(dirx * dirx + diry * diry);                 /* ENV:897 */
+        if (dist > 0) { fx += 2.0 * dirx / dist; fy += 2.0 * diry / dist; }  /* ENV:899 */
+        double avx = 0.0, avy = 0.0; int nn = 0;
+        for (int u = 0; u < K; ++u) {
+            const int j = neighbor_index[i * K + u];
+            if (j == -1) continue;                                           /* ENV:855-858 */
+            const double ddx = x - p[j], ddy = y - p[n + j];
+            const double dn = sqrt(ddx * ddx + ddy * ddy);
+            if (0 < dn && dn < P->r_avoid) {                                 /* ENV:916-919, repulsion_strength = 1.0 */
+                const double f = 1.0 * (P->r_avoid / dn - 1);
+                fx += f * (ddx / dn); fy += f * (ddy / dn);
+            }
+            avx += dp[j]; avy += dp[n + j]; ++nn;
+        }
+        if (nn > 0) {                                                        /* ENV:925-928 */
+            avx = avx / nn; avy = avy / nn;
+            fx += 2.0 * (avx - vx); fy += 2.0 * (avy - vy);
+        }
+        a[i] = fx < -1 ? -1 : (fx > 1 ? 1 : fx);                             /* np.clip, ENV:931 */
+        a[n + i] = fy < -1 ? -1 : (fy > 1 ? 1 : fy);
+    }
+}
+
 int orc_params_size(void) { return (int)sizeof(orc_params); }

@@ -131,6 +131,22 @@ class OracleBatch:
         return self.obs, self.reward, self.a_prior
 
 
+def strategy_actions(ob, kind):
+    """Actions of the reference's host strategies for the CURRENT state of an OracleBatch: kind 'rule' (assembly.py:530-601)
+    or 'llm' (assembly.py:524-529, 876-941; uses the neighbour list of the last observation).  [E, 2, n_a] float64."""
+    out = np.zeros((ob.E, 2, ob.n_a))
+    for e in range(ob.E):
+        P = ob.params[e]
+        g = np.ascontiguousarray(ob.grid_of(e))
+        if kind == "rule":
+            lib().orc_rule_actions(C.byref(P), _dp(ob.p[e]), _dp(ob.dp[e]), _dp(g), _dp(out[e]))
+        elif kind == "llm":
+            lib().orc_llm_actions(C.byref(P), _dp(ob.p[e]), _dp(ob.dp[e]), _dp(g), _ip(ob.neighbor_index[e]), _dp(out[e]))
+        else:
+            raise ValueError(kind)
+    return out
+
+
 def fill_actions(E, n_a, seed, step, env0=0):
     """U(-1,1) float32 [E,2,n_a] from the counter-based generator shared with the CUDA side."""
     act = np.empty((E, 2, n_a), dtype=np.float32)

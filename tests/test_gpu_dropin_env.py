@@ -149,3 +149,68 @@ def test_wrapper_metrics_match_the_reference_formulas(gym):
         assert abs(env.voronoi_based_uniformity() - ref3) <= 1e-12 * max(1.0, abs(ref3))
     assert occupied > 0
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,n_a,E", [("llm", 30, 48), ("rule", 30, 48), ("rule", 9, 16), ("llm", 64, 8)])
+def test_strategy_actions_match_the_oracle_restatement(kind, n_a, E):
+    """swarm_strategy_actions ('rule' assembly.py:530-601, 'llm' assembly.py:524-529/876-941) against the C restatement
+    that tests/test_oracle_vs_reference.py pins to the NumPy original at 1e-12: bit-identical for 'llm'; 'rule' may
+    differ in the last bits of the cosine weights (1e-13).  States come from a goal-seeking rollout (agents inside the
+    shapes, occupancy filter live) and from a small-r_avoid batch that exercises the 80-cell half-even subsample."""
+    import torch
+    from marl_llm_b200.batched import BatchedAssemblySim
+    from oracle import oracle as orc
+    from tests.helpers import goal_seeking_action, load_shapes, reset_like_reference
+    shapes = load_shapes()
+    ngm = int(shapes["n_g"].max())
+    for r_avoid, d_sen in ((orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"]), 0.4), (0.05, 0.6)):
+        rng = np.random.RandomState(17 + n_a)
+        sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True, d_sen=d_sen)
+        params, grids, P, DP = [], [], [], []
+        for e in range(E):
+            k, grid, p, dp = reset_like_reference(rng, n_a, shapes)
+            params.append(orc.make_params(n_a, grid.shape[1], float(shapes["l_cell"][k]), r_avoid, d_sen=d_sen))
+            grids.append(grid); P.append(p); DP.append(dp)
+        ob = orc.OracleBatch(params, nthreads=8)
+        for e in range(E):
+            ob.set_grid(e, grids[e])
+        ob.p[:], ob.dp[:] = np.stack(P), np.stack(DP)
+        blocks, n_g = sim.pack_grids(grids, ngm)
+        sim.set_grid(blocks, n_g, [q.l_cell for q in params])
+        sim.set_state(ob.p, ob.dp)
+        sim.observe(); ob.observe()
+        worst, used_sub = 0.0, 0
+        for t in range(40):
+            want = orc.strategy_actions(ob, kind)
+            got = sim.strategy_actions(kind).cpu().numpy()
+            if kind == "llm":
+                assert np.array_equal(got, want), t
+            else:
+                worst = max(worst, float(np.max(np.abs(got - want))))
+            used_sub += int(((ob.sensed_index >= 0).sum(2) == 80).sum())
+            a = goal_seeking_action(ob.obs, ob.dp, rng)
+            sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        assert worst < 1e-13, worst
+        assert ob.in_flags.sum() > 0
+        if d_sen == 0.6:
+            assert used_sub > 0
+
+
+@pytest.mark.gpu
+def test_dropin_env_runs_its_own_rule_strategy_like_collect_expert_data():
+    """collect_expert_data.py:110-113 sets agent_strategy='rule', is_collected=True: step() ignores the caller's action,
+    computes the controller on the device and returns it as the 5th output (assembly.py:663-664); the swarm assembles."""
+    from marl_llm_b200.assembly_env import AssemblySwarmEnv
+    args = make_args(30, agent_strategy="rule", is_collected=True)
+    env = AssemblySwarmEnv()
+    env.__reinit__(args)
+    np.random.seed(3)
+    env.reset()
+    inside = []
+    for t in range(250):
+        obs, rew, done, info, u = env.step(np.zeros((2, 30)))
+        assert u.shape == (2, 30) and np.all(np.abs(u) <= 1)
+        inside.append(float(np.mean(np.all(obs[28:30] == 0, axis=0))))       # target offset is zero iff in the shape (CPP:136-137)
+    # the reference with the same seed: in-shape fraction 0.45 over the first 20 steps, 1.0 over the last 20
+    assert np.mean(inside[:20]) < 0.7 and np.mean(inside[-20:]) > 0.95

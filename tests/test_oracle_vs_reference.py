@@ -117,3 +117,44 @@ def test_periodic_boundaries_match_reference(seed):
                            ("sen", ob.sensed_index[0], e.sensed_index), ("occ", ob.occupied_index[0], e.occupied_index)):
             assert np.array_equal(x, y, equal_nan=True), f"{name} differs at step {t}"
     assert wrapped > 10
+
+
+@pytest.mark.parametrize("strategy,n_a,seed", [("rule", 30, 4), ("rule", 12, 9), ("llm", 30, 6), ("llm", 8, 2)])
+def test_strategy_restatement_tracks_the_numpy_original(strategy, n_a, seed):
+    """agent_strategy 'rule' / 'llm' (assembly.py:519-601): the reference computes the action itself and returns it as the
+    5th output when is_collected (assembly.py:663-664).  The C restatement cannot be bit-identical to NumPy (BLAS dot with
+    FMA, pairwise np.sum, NumPy's own cos); it must agree to 1e-12 on the action of every step when fed the reference's
+    own state, including states inside the shape (the controllers drive the swarm there)."""
+    env = lr.make_env(n_a, agent_strategy=strategy, is_collected=True)
+    np.random.seed(seed)
+    env.reset()
+    e = env.env
+    P = orc.make_params(n_a, e.n_g, float(e.l_cell), float(e.r_avoid))
+    ob = orc.OracleBatch([P])
+    ob.set_grid(0, e.grid_center)
+    worst, in_shape, sub = 0.0, 0, 0
+    for t in range(150):
+        ob.p[0], ob.dp[0] = e.p, e.dp                      # the reference's own pre-step state
+        ob.neighbor_index[0] = e.neighbor_index
+        mine = orc.strategy_actions(ob, strategy)[0]
+        obs, rew, done, info, u = env.step(np.zeros((2, n_a)))
+        worst = max(worst, float(np.max(np.abs(mine - u))))
+        in_shape += int(e.in_flags.sum()); sub += int(((e.sensed_index >= 0).sum(1) == 80).sum())
+    assert worst < 1e-12, worst
+    assert in_shape > 0
+    # directed state for the 80-cell subsample of the rule controller (np.round = half-even, assembly.py:565): agents
+    # sitting on cells deep inside the shape with a small avoidance radius keep > 80 free cells in range
+    e.r_avoid, e.d_sen = 0.05, 0.6
+    P2 = orc.make_params(n_a, e.n_g, float(e.l_cell), 0.05, d_sen=0.6)
+    ob2 = orc.OracleBatch([P2]); ob2.set_grid(0, e.grid_center)
+    centre = e.grid_center.mean(axis=1, keepdims=True)
+    order = np.argsort(np.linalg.norm(e.grid_center - centre, axis=0))[:n_a * 3:3]
+    e.p = e.grid_center[:, order] + np.random.RandomState(seed).normal(0, 0.004, (2, n_a))
+    e.dp = np.random.RandomState(seed + 1).uniform(-0.2, 0.2, (2, n_a))
+    e._get_obs()                                            # refresh neighbor_index for the 'llm' strategy
+    ob2.p[0], ob2.dp[0], ob2.neighbor_index[0] = e.p, e.dp, e.neighbor_index
+    mine = orc.strategy_actions(ob2, strategy)[0]
+    n_free = [(np.linalg.norm(e.grid_center - e.p[:, [i]], axis=0) < e.d_sen).sum() for i in range(n_a)]
+    _, _, _, _, u = env.step(np.zeros((2, n_a)))
+    assert float(np.max(np.abs(mine - u))) < 1e-12
+    assert max(n_free) > 120                                # far above the cap of 80 even after the occupancy filter
