@@ -48,13 +48,15 @@ double thresh_le(double h) {
 
 int round32(int n) { return (n + 31) & ~31; }
 
-size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs) {
+size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0) {
     (void)n_g_pad;
     size_t b = (size_t)2 * CHUNK_CELLS * sizeof(double2) + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
-    b += (size_t)TOPO * nt * sizeof(int);                                                           // neighbour list
-    b += (size_t)nt * sizeof(float2);                                                                // fp32 positions (pair-loop filter)
+    if (phase != 2) {                                                                                // the second-half kernel parks its neighbour list on the idle ring
+        b += (size_t)TOPO * nt * sizeof(int);                                                       // neighbour list
+        b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
+    }
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
     if (nt == 32 && n_words <= 32 && scratch > (size_t)2 * CHUNK_CELLS * sizeof(double2)) b += scratch;   // aliases the TMA ring when it fits
     return b;
@@ -119,7 +121,8 @@ struct swarm_sim {
     KParams K;
     int nt;                 // threads per CTA
     bool split;             // step = two launches (k_step PH 1 + PH 2)
-    size_t smem;
+    size_t smem;            // dynamic shared memory of k_step PH 0 / 1
+    size_t smem2;           // ... of the second-half kernel (PH 2)
     int pending;            // a_prior buffer holding the prior of the CURRENT state
     int last;               // a_prior buffer returned by the most recent step
     bool prior_dirty;       // state / grid changed behind the kernel's back
@@ -187,6 +190,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
     s->nt = round32(cfg->n_a);
     s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max);
+    s->smem2 = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max, 2);
     if (const char *x = getenv("SWARM_DEBUG_EXTRA_SMEM")) s->smem += (size_t)atoi(x);   // occupancy experiments only
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete s;
@@ -197,7 +201,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
         for (int ph = 0; ph < 3; ++ph) {
             if (ph > 0 && s->nt > 128) continue;
             step_fn_t f = pick_step(cfg->out_dtype == SWARM_F32, dyn != 0, cfg->emit_indices != 0, s->nt, ph);
-            cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem);
+            cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ph == 2 ? s->smem2 : s->smem));
             if (e != cudaSuccess) { delete s; return fail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
         }
     s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
@@ -348,7 +352,7 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
     if (s->split) {
         pick_step(f32, dyn, emit, s->nt, 1)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
-        pick_step(f32, dyn, emit, s->nt, 2)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+        pick_step(f32, dyn, emit, s->nt, 2)<<<s->cfg.num_envs, s->nt, s->smem2, st>>>(K);
         s->launches += 2;
     } else {
         pick_step(f32, dyn, emit, s->nt, 0)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
