@@ -387,7 +387,10 @@ def main():
     # ---- widened path: replay push, on-device policy, whole device-resident rollout loop (rank 0, N=1) ----
     extras = None
     if rank == 0 and world == 1 and not args.no_extras and not parity and n_a == 30:
-        extras = widened_path_numbers(torch, sim, acts[0], peak)
+        try:
+            extras = widened_path_numbers(torch, sim, acts[0], peak)
+        except Exception as ex:            # the widened-path numbers must never cost the main line
+            extras = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank == 0:
         line = {
