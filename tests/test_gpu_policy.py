@@ -138,3 +138,28 @@ def test_split_fp16_tensor_core_policy_is_fp32_accurate(E, n_a):
     torch.testing.assert_close(act.cpu(), exact, rtol=1e-5, atol=1e-5)   # 1e-5 of the (-1, 1) action range; observed max 6e-6
     act2, _ = pol.step(obs.cuda())
     assert torch.equal(act, act2)                               # deterministic
+
+
+@pytest.mark.parametrize("prec,atol", [("f16x3_tc", 1e-5), ("f16_tc", 5e-3)])
+@pytest.mark.parametrize("E,n_a,D,H,A", [(9, 30, 188, 180, 2), (4, 50, 192, 64, 3), (2, 33, 100, 192, 4), (1, 5, 16, 8, 1)])
+def test_tensor_core_paths_with_other_network_sizes(prec, atol, E, n_a, D, H, A):
+    """Zero padding of the tensor-core paths: obs_dim < 192 (is_con_self_state=False gives 188), hidden < 192, act_dim 1..4
+    (partial outputs exchanged between the two epilogue warps of a row)."""
+    torch.manual_seed(E * 100 + A)
+    ref = RefMLP(D, A, H)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.mul_(2.0)
+    obs = torch.randn(E, D, n_a) * 0.6
+    pol = DevicePolicy(D, A, H, precision=prec).load_state_dict(ref.state_dict())
+    act, _ = pol.step(obs.cuda())
+    with torch.no_grad():
+        want = ref(obs.permute(0, 2, 1).reshape(E * n_a, D)).reshape(E, n_a, A).permute(0, 2, 1)
+    torch.testing.assert_close(act.cpu(), want, rtol=1e-5 if prec == "f16x3_tc" else 0, atol=atol)
+
+
+def test_tensor_core_path_rejects_wide_actions():
+    from marl_llm_b200._lib import SwarmError
+    pol = DevicePolicy(192, 6, 180)
+    with pytest.raises(SwarmError):
+        pol.set_precision("f16_tc")
