@@ -227,6 +227,23 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
         buf.push(prev, act2, rew, nxt, done, idx, prior, lp)
         obs_pair[0], obs_pair[1] = spare, prev
     loop_ms = timed(loop_step, 20)
+
+    from marl_llm_b200.episode_ring import EpisodeRing
+    del buf
+    ring = EpisodeRing(4, E, n_a, D, A)
+    state = {"t": 0}
+
+    def ring_step():                       # time-indexed ring: the policy kernel writes the replay rows, only small arrays are pushed
+        prev, spare = obs_pair
+        if state["t"] == ring.T:
+            ring.begin(); state["t"] = 0
+        _, lp = pol.step(prev, explore=True, out=act2, rows_out=ring.slot(state["t"]))
+        sim.set_obs_buffer(spare)
+        nxt, rew, done, _, prior = sim.step(act2)
+        ring.record(state["t"], act2, rew, done, prior, lp)
+        state["t"] += 1
+        obs_pair[0], obs_pair[1] = spare, prev
+    ring_ms = timed(ring_step, 20)
     flop = 2.0 * rows * (D * H + 2 * H * H + H * A)
     return {
         "rollout_push": {"kernel": "swarm::k_rollout_push_tma", "ms": push_ms, "GBps": push_bytes / push_ms / 1e6,
@@ -237,6 +254,8 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
         "policy_f16_tc": {"kernel": "swarm::k_policy_mlp_tc (tcgen05, TMEM)", "ms": pol_tc_ms, "TFLOPs": flop / pol_tc_ms / 1e9},
         "device_rollout_loop": {"stages": "policy(f16_tc) -> step -> push, obs double-buffered", "ms_per_step": loop_ms,
                                 "agent_steps_per_s": rows / loop_ms * 1e3},
+        "device_rollout_loop_ring": {"stages": "policy(f16_tc, writes the replay rows) -> step -> small-array push (time-indexed ring)",
+                                     "ms_per_step": ring_ms, "agent_steps_per_s": rows / ring_ms * 1e3},
     }
 
 

@@ -243,6 +243,17 @@ int swarm_rollout_push(const swarm_rollout_buffers *buf, int64_t row0, int32_t n
                        int32_t agent_stop, const void *obs, const void *next_obs, const void *reward, const uint8_t *done,
                        const void *act_prior, int out_dtype, const void *act, int act_dtype, const float *log_pi, void *stream);
 
+/* The same push in parts (SWARM_PUSH_* bit mask): lets a time-indexed ring (obs of step t+1 = next_obs of step t, one
+ * array) store each observation once — SWARM_PUSH_OBS alone transposes `obs` into ring rows [row0, ...), SWARM_PUSH_SMALL
+ * alone writes act / act_prior / reward / done / log_pi.  Inputs of parts that are not requested may be NULL. */
+#define SWARM_PUSH_OBS 1
+#define SWARM_PUSH_NEXT_OBS 2
+#define SWARM_PUSH_SMALL 4
+int swarm_rollout_push_parts(const swarm_rollout_buffers *buf, int64_t row0, int32_t num_envs, int32_t n_a, int32_t agent_start,
+                             int32_t agent_stop, const void *obs, const void *next_obs, const void *reward, const uint8_t *done,
+                             const void *act_prior, int out_dtype, const void *act, int act_dtype, const float *log_pi, int parts,
+                             void *stream);
+
 /* the gather of sample(), BUF:152-161: rows_dev [n] int64 ring rows (device) -> [n][dim] f32 outputs (device);
  * act_prior / log_pi outputs may be NULL (BUF:159-162 is_prior / is_log_pi). */
 int swarm_rollout_gather(const swarm_rollout_buffers *buf, const int64_t *rows_dev, int32_t n, float *obs, float *act, float *reward,
@@ -282,6 +293,15 @@ int swarm_policy_set_precision(swarm_policy *p, int precision);
  * layer1_acc_dev [E*n_a][192] f32 (device). */
 int swarm_policy_debug_buffer(swarm_policy *p, float *layer1_acc_dev);
 int64_t swarm_policy_launch_count(const swarm_policy *p);
+
+/* gather for a time-indexed ring: next_obs of ring row r is row r + next_row_offset of the OBS array (buf->next_obs may be
+ * NULL); next_row_offset < 0 behaves like swarm_rollout_gather. */
+int swarm_rollout_gather_ring(const swarm_rollout_buffers *buf, const int64_t *rows_dev, int32_t n, int64_t next_row_offset, float *obs,
+                              float *act, float *reward, float *next_obs, float *done, float *act_prior, float *log_pi, void *stream);
+
+/* While non-NULL, swarm_policy_step also writes every agent's observation as one fp32 row, rows_dev [E*n_a][obs_dim] (device):
+ * the transposition a replay push would do, for free, from the registers of the threads that read the observation anyway. */
+int swarm_policy_rows_out(swarm_policy *p, float *rows_dev);
 
 const char *swarm_last_error(void);
 int swarm_abi_version(void);

@@ -44,9 +44,10 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
                    "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho"]
-ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather"]
+ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather", "swarm_rollout_push_parts", "swarm_rollout_gather_ring"]
+SWARM_PUSH_OBS, SWARM_PUSH_NEXT_OBS, SWARM_PUSH_SMALL = 1, 2, 4
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
-                  "swarm_policy_set_precision", "swarm_policy_debug_buffer"]
+                  "swarm_policy_set_precision", "swarm_policy_debug_buffer", "swarm_policy_rows_out"]
 SWARM_POLICY_FP32, SWARM_POLICY_F16_TC, SWARM_POLICY_F16X3_TC = 0, 1, 2
 
 
@@ -99,6 +100,11 @@ def load():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                        C.c_void_p, C.c_void_p]
     lib.swarm_rollout_gather.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+    lib.swarm_rollout_push_parts.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_void_p]
+    lib.swarm_rollout_gather_ring.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
+    lib.swarm_policy_rows_out.argtypes = [C.c_void_p, C.c_void_p]
     lib.swarm_policy_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
     lib.swarm_policy_destroy.argtypes = [C.c_void_p]
     lib.swarm_policy_load.argtypes = [C.c_void_p] + [C.c_void_p] * 8

@@ -27,6 +27,7 @@ constexpr int POL_AMAX = 8;      // largest action dimension
 
 struct PolicyParams {
     const float *obs; float *act; float *log_pi;        // log_pi [E][1][n_a] or NULL
+    float *rows_out;             // optional [E*n_a][K0]: every agent's observation as one row (replay storage for free), or NULL
     long n_cols;                 // E * n_a
     int n_a, K0, A;              // agents per env, observation features (<= POL_HP), action dimension (<= POL_AMAX)
     const float *Wt[3];          // [POL_HP][POL_HP] transposed weights Wt[k][n] of the three hidden layers, zero-padded
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy_mlp(const PolicyParam
         if (k < P.K0 && col < P.n_cols) {
             const long e = col / n_a; const int a = (int)(col - e * n_a);
             v = P.obs[(e * P.K0 + k) * n_a + a];
+            if (P.rows_out) P.rows_out[col * P.K0 + k] = v;
         }
         hA[idx] = v;
     }
@@ -341,6 +343,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                     const int k = k_lo + c * 32 + q;
                     f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                 }
+                if (P.rows_out && valid) {                                // the row chunk this thread holds: 128 contiguous bytes
+                    float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;
+                    if ((P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(rw)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) if (k_lo + c * 32 + q < P.K0) rw[q] = f[q];
+                    }
+                }
                 uint32_t r[16];
 #pragma unroll
                 for (int q = 0; q < 16; ++q) r[q] = pack_h2(f[2 * q], f[2 * q + 1]);
@@ -586,6 +598,16 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTc
                 for (int q = 0; q < 32; ++q) {
                     const int k = k_lo + c * 32 + q;
                     f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
+                }
+                if (P.rows_out && valid) {
+                    float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;
+                    if ((P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) reinterpret_cast<float4 *>(rw)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) if (k_lo + c * 32 + q < P.K0) rw[q] = f[q];
+                    }
                 }
                 uint32_t rh[16], rl[16];
 #pragma unroll

@@ -32,6 +32,7 @@ struct PushParams {
     const float *log_pi;       // [E][1][n_a] or NULL
     const unsigned char *done; // [E][1][n_a] (bool)
     int out_f32, act_f32;
+    int parts;                 // bit 0: transpose obs, bit 1: transpose next_obs, bit 2: the small per-agent arrays
 };
 
 __device__ __forceinline__ float ldf(const void *p, int is_f32, size_t k) {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_rollout_push(const PushParams 
     const int D = P.B.obs_dim, n_a = P.n_a;
     const long row = P.row0 + (long)e * span + (long)blockIdx.y * PUSH_CHUNK;   // ring row of agent c0 (BUF:86-90: rows follow agent order)
     for (int pass = 0; pass < 2; ++pass) {
+        if (!(P.parts & (1 << pass))) continue;
         const void *src = pass ? P.next_obs : P.obs;
         float *dst = (pass ? P.B.next_obs : P.B.obs) + row * D;
         const size_t base = (size_t)e * D * n_a;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_rollout_push(const PushParams 
         }
         __syncthreads();
     }
+    if (!(P.parts & 4)) return;
     const int A = P.B.act_dim;
     for (int k = threadIdx.x; k < A * nc; k += PUSH_THREADS) {
         const int a = k / A, d = k - a * A;
@@ -104,21 +107,24 @@ __device__ __forceinline__ uint32_t rsmem_u32(const void *p) { return (uint32_t)
 __global__ void __launch_bounds__(PUSH_THREADS) k_rollout_push_tma(const PushParams P) {
     extern __shared__ __align__(128) float tile[];        // [D*n_a] in, [n_a*D] out
     __shared__ __align__(8) uint64_t bar;
-    const int e = blockIdx.x, pass = blockIdx.y;
+    const int e = blockIdx.x;
+    const int npass = (P.parts & 1) + ((P.parts >> 1) & 1);        // grid.y = max(npass, 1)
+    const int pass = npass == 2 ? (int)blockIdx.y : (npass == 1 ? ((P.parts & 1) ? 0 : 1) : -1);
+    const bool do_small = (P.parts & 4) && blockIdx.y == 0;
     const int D = P.B.obs_dim, n_a = P.n_a, n = D * n_a;
     const unsigned bytes = (unsigned)n * 4u;
     float *tin = tile, *tout = tile + n;
     const long row = P.row0 + (long)e * n_a;
-    const float *src = reinterpret_cast<const float *>(pass ? P.next_obs : P.obs) + (size_t)e * n;
-    float *dst = (pass ? P.B.next_obs : P.B.obs) + row * D;
-    if (threadIdx.x == 0) {
+    const float *src = reinterpret_cast<const float *>(pass == 1 ? P.next_obs : P.obs) + (size_t)e * n;
+    float *dst = (pass == 1 ? P.B.next_obs : P.B.obs) + row * D;
+    if (pass >= 0 && threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rsmem_u32(&bar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rsmem_u32(&bar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(rsmem_u32(tin)), "l"(src), "r"(bytes), "r"(rsmem_u32(&bar)) : "memory");
     }
-    if (pass == 0) {                                      // the small per-agent arrays ride along while the copy is in flight
+    if (do_small) {                                       // the small per-agent arrays ride along while the copy is in flight
         const int A = P.B.act_dim;
         for (int k = threadIdx.x; k < A * n_a; k += PUSH_THREADS) {
             const int a = k / A, d = k - a * A;
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_rollout_push_tma(const PushPar
             if (P.log_pi && P.B.log_pi) P.B.log_pi[row + a] = P.log_pi[s_];
         }
     }
+    if (pass < 0) return;                                 // small arrays only
     __syncthreads();                                      // barrier initialised before anyone polls it
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
@@ -160,11 +167,30 @@ __global__ void __launch_bounds__(PUSH_THREADS) k_rollout_push_tma(const PushPar
     }
 }
 
+// The small per-agent arrays alone (time-indexed ring: the observations are written elsewhere): one thread per agent row.
+__global__ void __launch_bounds__(256) k_rollout_push_small(const PushParams P, long n_rows) {
+    const int span = P.a1 - P.a0, A = P.B.act_dim, n_a = P.n_a;
+    for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < n_rows; r += (long)gridDim.x * blockDim.x) {
+        const long e = r / span; const int a = P.a0 + (int)(r - e * span);
+        const long row = P.row0 + r;
+        for (int d = 0; d < A; ++d) {
+            const size_t s_ = (size_t)e * A * n_a + (size_t)d * n_a + a;
+            P.B.act[row * A + d] = ldf(P.act, P.act_f32, s_);
+            if (P.prior && P.B.act_prior) P.B.act_prior[row * A + d] = ldf(P.prior, P.out_f32, s_);
+        }
+        const size_t s1 = (size_t)e * n_a + a;
+        P.B.rew[row] = ldf(P.rew, P.out_f32, s1);
+        P.B.done[row] = P.done[s1] ? 1.0f : 0.0f;
+        if (P.log_pi && P.B.log_pi) P.B.log_pi[row] = P.log_pi[s1];
+    }
+}
+
 struct GatherParams {
     RolloutBuf B;
     const long *idx;           // [n] ring rows (device)
     int n;
     float *obs, *act, *rew, *next_obs, *done, *prior, *log_pi;   // [n][dim] outputs; prior / log_pi may be NULL
+    long next_off;             // >= 0: next_obs of row r is row r + next_off of the OBS array (time-indexed ring); < 0: the next_obs array
 };
 
 __global__ void __launch_bounds__(256) k_rollout_gather(const GatherParams P) {
@@ -172,12 +198,13 @@ __global__ void __launch_bounds__(256) k_rollout_gather(const GatherParams P) {
     if (warp >= P.n) return;
     const long r = P.idx[warp];
     const int D = P.B.obs_dim, A = P.B.act_dim;
+    const float *nsrc = P.next_off >= 0 ? P.B.obs + (r + P.next_off) * D : P.B.next_obs + r * D;
     if ((D & 3) == 0) {                                    // rows are 16-byte aligned: vector copies
-        const float4 *s0 = reinterpret_cast<const float4 *>(P.B.obs + r * D), *s1 = reinterpret_cast<const float4 *>(P.B.next_obs + r * D);
+        const float4 *s0 = reinterpret_cast<const float4 *>(P.B.obs + r * D), *s1 = reinterpret_cast<const float4 *>(nsrc);
         float4 *d0 = reinterpret_cast<float4 *>(P.obs + (size_t)warp * D), *d1 = reinterpret_cast<float4 *>(P.next_obs + (size_t)warp * D);
         for (int k = lane; k < D / 4; k += 32) { d0[k] = s0[k]; d1[k] = s1[k]; }
     } else {
-        for (int k = lane; k < D; k += 32) { P.obs[(size_t)warp * D + k] = P.B.obs[r * D + k]; P.next_obs[(size_t)warp * D + k] = P.B.next_obs[r * D + k]; }
+        for (int k = lane; k < D; k += 32) { P.obs[(size_t)warp * D + k] = P.B.obs[r * D + k]; P.next_obs[(size_t)warp * D + k] = nsrc[k]; }
     }
     for (int k = lane; k < A; k += 32) {
         P.act[(size_t)warp * A + k] = P.B.act[r * A + k];

@@ -66,7 +66,7 @@ class DevicePolicy:
     def scale_noise(self, scale):                       # agents.py:60-67
         self.scale = float(scale)
 
-    def step(self, obs, explore=False, out=None, want_log_pi=True):
+    def step(self, obs, explore=False, out=None, want_log_pi=True, rows_out=None):
         """agents.py:69-96.  Returns (action, log_pi): [E, act_dim, n_a], [E, 1, n_a] (leading axis dropped for 2-D input)."""
         if not (isinstance(obs, torch.Tensor) and obs.is_cuda and obs.dtype == torch.float32):
             raise TypeError("DevicePolicy.step takes the simulator's fp32 CUDA observation tensor")
@@ -80,6 +80,10 @@ class DevicePolicy:
         mode = 0
         if explore:                                     # agents.py:85-86: ONE draw per step decides the branch for the whole batch
             mode = 2 if np.random.rand() < self.epsilon else 1
+        if rows_out is not None:        # agent-major copy of the observations ([E * n_a, obs_dim] fp32): replay storage for free
+            assert rows_out.is_cuda and rows_out.dtype == torch.float32 and rows_out.is_contiguous() and rows_out.numel() == E * n_a * D
+        check(self.lib.swarm_policy_rows_out(self._h, C.c_void_p(rows_out.data_ptr()) if rows_out is not None else None),
+              "swarm_policy_rows_out")
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         check(self.lib.swarm_policy_step(self._h, C.c_void_p(o.data_ptr()), E, n_a, C.c_void_p(act.data_ptr()),
                                          C.c_void_p(log_pi.data_ptr()) if want_log_pi else None, mode, self.scale, self.seed,

@@ -29,3 +29,23 @@ def rollout(sim, policy, buffer, steps, explore=True, index=None):
         mean_rew[t] = rew.double().mean()
         obs_prev, spare = next_obs, obs_prev
     return mean_rew
+
+
+def rollout_ring(sim, policy, ring, steps, explore=True):
+    """The same loop on a time-indexed ring (marl_llm_b200/episode_ring.py): the policy kernel writes each step's
+    observations as replay rows while it reads them, env.step follows, and only the small per-agent arrays are pushed —
+    no observation transposes in the loop.  Returns the per-step mean reward ([steps] float64 CUDA tensor)."""
+    assert steps <= ring.T and sim.out_dtype == torch.float32
+    ring.begin()
+    obs_prev, spare = sim.obs, torch.empty_like(sim.obs)
+    act = torch.empty(sim.E, policy.act_dim, sim.n_a, dtype=torch.float32, device=sim.device)
+    mean_rew = torch.zeros(steps, dtype=torch.float64, device=sim.device)
+    for t in range(steps):
+        _, log_pi = policy.step(obs_prev, explore=explore, out=act, rows_out=ring.slot(t))
+        sim.set_obs_buffer(spare)
+        next_obs, rew, done, _, prior = sim.step(act)
+        ring.record(t, act, rew, done, prior, log_pi)
+        mean_rew[t] = rew.double().mean()
+        obs_prev, spare = next_obs, obs_prev
+    ring.close(obs_prev)
+    return mean_rew

@@ -110,3 +110,44 @@ def test_device_rollout_loop_fills_the_buffer_consistently():
     assert torch.equal(buf.next_obs_buffs[(T - 1) * n:], rows(sim.obs))
     assert torch.equal(buf.rew_buffs[(T - 1) * n:], rows(sim.reward)) and torch.equal(buf.ac_prior_buffs[(T - 1) * n:], rows(sim.a_prior))
     assert float(buf.ac_buffs.abs().max()) <= 1.0 and float(buf.log_pi_buffs.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16_tc", "f16x3_tc"])
+def test_time_indexed_ring_equals_the_conventional_buffer(prec):
+    """EpisodeRing (observations stored once, rows written by the policy kernel) against ReplayBufferAgent (obs and next_obs
+    transposed by the push) for the same seeded rollout: identical transitions, for every policy kernel."""
+    import torch.nn as nn
+    from marl_llm_b200.batched import BatchedAssemblySim, r_avoid_for
+    from marl_llm_b200.episode_ring import EpisodeRing
+    from marl_llm_b200.policy import DevicePolicy
+    from marl_llm_b200.rollout_loop import rollout, rollout_ring
+    from tests.helpers import load_shapes
+    shapes = load_shapes()
+    E, n_a, T = 21, 30, 5
+    n = E * n_a
+    torch.manual_seed(0)
+    sd = {}
+    for name, (o, i) in (("fc1", (180, 192)), ("fc2", (180, 180)), ("fc3", (180, 180)), ("fc4", (2, 180))):
+        l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
+    outs = []
+    for kind in ("buffer", "ring"):
+        sim = BatchedAssemblySim(E, n_a, int(shapes["n_g"].max()), r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"]))
+        sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+        sim.reset(seed=8)
+        pol = DevicePolicy(192, 2, 180, noise_scale=0.3, seed=5, precision=prec).load_state_dict(sd)
+        if kind == "buffer":
+            store = ReplayBufferAgent(T, n, slice(0, n_a), 192, 2)
+            rollout(sim, pol, store, T)
+            outs.append(store.gather(np.arange(T * n), is_prior=True, is_log_pi=True))
+        else:
+            ring = EpisodeRing(T, E, n_a, 192, 2)
+            assert len(ring) == 0
+            rollout_ring(sim, pol, ring, T)
+            assert len(ring) == T * n and ring.closed
+            outs.append(ring.gather(np.arange(T * n), is_prior=True, is_log_pi=True))
+            smp = ring.sample(64, is_prior=True)
+            assert smp[0].shape == (64, 192) and smp[5].shape == (64, 2) and smp[6] is None
+            with pytest.raises(IndexError):
+                ring.gather([T * n])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

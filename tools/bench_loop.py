@@ -32,6 +32,22 @@ def one():
     nxt, rew, done, _, prior = sim.step(act)
     buf.push(prev, act, rew, nxt, done, idx, prior, lp)
     pair[0], pair[1] = spare, prev
+if len(sys.argv) > 2 and sys.argv[2] == "ring":
+    from marl_llm_b200.episode_ring import EpisodeRing
+    del buf
+    ring = EpisodeRing(8, E, n_a, D, A)
+    state = {"t": 0}
+    def one():                                        # noqa: F811
+        prev, spare = pair
+        t = state["t"]
+        if t == ring.T:
+            ring.begin(); t = 0
+        _, lp = pol.step(prev, explore=True, out=act, rows_out=ring.slot(t))
+        sim.set_obs_buffer(spare)
+        nxt, rew, done, _, prior = sim.step(act)
+        ring.record(t, act, rew, done, prior, lp)
+        state["t"] = t + 1
+        pair[0], pair[1] = spare, prev
 for _ in range(20): one()
 torch.cuda.synchronize()
 K = 50
@@ -40,5 +56,5 @@ e0.record()
 for _ in range(K): one()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / K
-print(json.dumps({"loop": "policy(%s) -> step -> push (obs double-buffered)" % prec, "envs": E, "n_a": n_a, "ms_per_step": ms,
+print(json.dumps({"loop": ("policy(%s, rows_out) -> step -> small push (time-indexed ring)" if len(sys.argv) > 2 else "policy(%s) -> step -> push (obs double-buffered)") % prec, "envs": E, "n_a": n_a, "ms_per_step": ms,
                   "agent_steps_per_s": E * n_a / ms * 1e3, "mean_reward": float(sim.reward.mean())}))
