@@ -59,9 +59,11 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     if (e != cudaSuccess) { delete p; return pfail(SWARM_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     if (e == cudaSuccess) e = cudaMalloc(&p->d_w16, (size_t)3 * TC_W_BYTES);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_w16x, (size_t)6 * TC_W_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
     if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POL_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void *)k_policy_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(TC_AMAX));
     if (e != cudaSuccess) { cudaFree(p->d_w); cudaFree(p->d_w16); cudaFree(p->d_w16x); delete p; return pfail(SWARM_ERR_CUDA, std::string("policy setup: ") + cudaGetErrorString(e)); }
     *out = p;
     return SWARM_OK;
@@ -147,7 +149,8 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
         Q.base = P; Q.w16 = p->d_w16x; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
         Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
         const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
-        k_policy_mlp_tc3<<<grid, T3_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
+        if (p->rows_out) k_policy_mlp_tc3<true><<<grid, T3_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
+        else k_policy_mlp_tc3<false><<<grid, T3_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
         PCU_TRY(cudaGetLastError());
         p->launches++;
         return SWARM_OK;
@@ -157,7 +160,8 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
         Q.base = P; Q.w16 = p->d_w16; Q.small = p->d_w + (size_t)3 * POL_HP * POL_HP; Q.debug = p->debug;
         Q.n_tiles = (P.n_cols + TC_M - 1) / TC_M;
         const unsigned grid = (unsigned)(Q.n_tiles < p->n_sm ? Q.n_tiles : p->n_sm);     // persistent: one CTA per SM
-        k_policy_mlp_tc<<<grid, TC_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
+        if (p->rows_out) k_policy_mlp_tc<true><<<grid, TC_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
+        else k_policy_mlp_tc<false><<<grid, TC_THREADS, tc_smem_bytes(p->act_dim), (cudaStream_t)stream>>>(Q);
         PCU_TRY(cudaGetLastError());
         p->launches++;
         return SWARM_OK;

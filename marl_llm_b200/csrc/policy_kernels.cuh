@@ -263,6 +263,7 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {      // arrives on ba
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
 
+template <bool ROWS>   // ROWS: the loaders also write every agent's observation as a replay row (swarm_policy_rows_out)
 __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcParams Q) {
     extern __shared__ __align__(128) unsigned char tsm[];
     unsigned char *sW = tsm;                                             // 3 layers of weights
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                     const int k = k_lo + c * 32 + q;
                     f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                 }
-                if (P.rows_out && valid) {                                // the row chunk this thread holds: 128 contiguous bytes
+                if (ROWS && valid) {                                // the row chunk this thread holds: 128 contiguous bytes
                     float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;
                     if ((P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
 #pragma unroll
@@ -510,6 +511,7 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_
     hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
+template <bool ROWS>
 __global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTcParams Q) {
     extern __shared__ __align__(128) unsigned char tsm[];
     unsigned char *sW = tsm;                                             // 3 ring slots of TC_W_BYTES
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTc
                     const int k = k_lo + c * 32 + q;
                     f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                 }
-                if (P.rows_out && valid) {
+                if (ROWS && valid) {
                     float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;
                     if ((P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
 #pragma unroll
