@@ -479,7 +479,7 @@ def test_config3_full_size_65536_envs_properties():
     depend on its neighbours in the batch); (2) the same batch stepped by a second simulator gives identical tensors
     (determinism: checksum of every output); (3) observe() is idempotent; (4) done stays False, rewards are 0/1."""
     import bench
-    E, n_a, steps = 65536, 30, 25
+    E, n_a, steps = 65536, 30, 200                               # a whole episode (CFG:181), the north star's rollout length
     shapes = load_shapes()
     ngm = int(shapes["n_g"].max())
     r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
