@@ -66,7 +66,7 @@ def synth_batch(E, n_a, shapes, seed, regime):
         blocks[sel, :ng] = gx
         blocks[sel, ng:2 * ng] = gy
         if regime == "converged":
-            pick = np.stack([rng.choice(ng, n_a, replace=False) for _ in sel])
+            pick = np.stack([rng.choice(ng, n_a, replace=n_a > ng) for _ in sel])
             p[sel, 0] = np.take_along_axis(gx, pick, 1) + rng.normal(0, 0.01, pick.shape)
             p[sel, 1] = np.take_along_axis(gy, pick, 1) + rng.normal(0, 0.01, pick.shape)
     if regime != "converged":
@@ -270,7 +270,9 @@ def main():
     ap.add_argument("--n-a", dest="n_a", type=int, default=30)
     ap.add_argument("--layout", default="production", choices=["production", "parity"],
                     help="production: fp64 state, fp32 obs/reward/prior; parity: everything fp64 + index arrays")
-    ap.add_argument("--regime", default="random", choices=["random", "converged"])
+    ap.add_argument("--regime", default="both", choices=["both", "random", "converged"],
+                    help="headline = the first regime run (random: U(-1,1) actions, staggered 200-step episodes with auto-reset)")
+    ap.add_argument("--episode-length", type=int, default=200, help="CFG:181")
     ap.add_argument("--brute-force-scan", action="store_true", help="A/B: disable the word-box culling of the grid scan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -313,58 +315,107 @@ def main():
     sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, device=local_rank,
                              out_dtype=torch.float64 if parity else torch.float32, emit_indices=parity,
                              brute_force_scan=args.brute_force_scan)
+    sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
     env0, _ = shard_range(world * E, rank, world)                       # this rank's global env ids: [env0, env0 + E)
-    blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, args.regime)   # shard = own seed = own envs
-    sim.set_grid(blocks, n_g, l_cell)
-    sim.set_state(p, dp)
-    sim.observe()
+    sim.n_g[:] = int(np.mean(shapes["n_g"]))                            # mean cell count (roofline bytes); per-env counts live on the device
 
     K, W = args.steps, args.warmup
-    ring = min(K + W, 16)
+    ring = 16
     acts = torch.empty(ring, E, 2, n_a, dtype=torch.float32, device="cuda")
     for r in range(ring):
         sim.fill_actions(acts[r], seed=226, step=r, env_offset=env0)
-    torch.cuda.synchronize()
-
-    for t in range(W):
-        sim.step(acts[t % ring])
-    barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
-    l0 = sim.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for t in range(K):
-        sim.step(acts[(W + t) % ring])
-    ev1.record()
-    barrier()
-    launches = sim.launch_count - l0
-    ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
-    ms = max_over_ranks(ms, device="cuda")
-    stats = all_reduce_stats(episode_stats(sim.reward, sim.in_flags)).tolist()   # optional episode statistics (not timed)
-    value = world * E * n_a * K / (ms * 1e-3)
-
-    # ---- roofline of the dominant (only) kernel ----
-    bytes_per_agent = sim.algorithmic_bytes_per_agent_step()
-    bytes_per_launch = bytes_per_agent * E * n_a
-    launch_ms = ms / K
-    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    EP = args.episode_length
+    lists = [torch.arange(ph, E, EP, dtype=torch.int32, device="cuda") for ph in range(EP)]
+    clock = {"t": 0}
     peak, peak_src = measured_hbm_peak()
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": ("swarm::k_step<PH=1> + swarm::k_step<PH=2> (one step = two launches; the second is the dominant one)"
-                           if launches == 2 * K else "swarm::k_step"), "launch_ms": launch_ms,
-                "algorithmic_bytes_per_agent_step": bytes_per_agent}
+
+    def step_random():
+        """One step of the 'random' regime: U(-1,1) actions (BASELINE config 1/3) for every env, then the auto-reset of the
+        envs whose 200-step episode (CFG:181) just ended.  Env e resets when t = e (mod 200), so the batch is a stationary
+        mixture of episode ages and the measured rate does not depend on where the timed window starts or how long it is."""
+        t = clock["t"]
+        sim.step(acts[t % ring])
+        due = lists[t % EP]
+        if due.numel():
+            sim.reset_envs(due, seed=226, episode=1 + t, env_offset=env0)
+        clock["t"] = t + 1
+
+    def step_converged():
+        """One step of the 'converged' regime: every agent follows the prior policy from a state in which the swarm already
+        fills its shape (what training converges to): all agents in-shape, ~75 sensed cells, occupancy filter and psi sums live."""
+        sim.step(sim.a_prior)
+
+    def timed(step_fn, k, w):
+        for _ in range(w):
+            step_fn()
+        barrier()
+        l0 = sim.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(k):
+            step_fn()
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1), device="cuda"), sim.launch_count - l0
+
+    def roofline_of(ms_per_step):
+        """HBM for the 30-agent configurations (algorithmic bytes: 1126 B per agent-step in the production
+        layout at n_g = 512), the FP32 pipe for the O(n_a^2) large-swarm configuration (6 n_a + 6 n_g flops per agent-step)."""
+        if n_a <= 128:
+            b = sim.algorithmic_bytes_per_agent_step(survey=True)
+            achieved = b * E * n_a / (ms_per_step * 1e-3) / 1e9
+            ext = sim.algorithmic_bytes_per_agent_step(survey=False)
+            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "launch_ms": ms_per_step, "algorithmic_bytes_per_agent_step": b,
+                    "bytes_per_agent_step_incl_neighbor_index_and_seed": ext,
+                    "frac_incl_neighbor_index_and_seed": ext * E * n_a / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "kernel": "swarm::k_step<PH=1> + swarm::k_step<PH=2> (one step = two launches; the second is the dominant one)"}
+        f32, f64 = sim.measure_fma_peak()
+        flops = 6.0 * n_a + 6.0 * float(np.mean(shapes["n_g"]))
+        achieved = flops * E * n_a / (ms_per_step * 1e-3) / 1e12
+        return {"bound": "fp32", "achieved": achieved, "peak": f32, "unit": "TFLOP/s", "frac": achieved / f32, "traffic": None,
+                "peak_source": "measured here: register-resident FMA loop (swarm_measure_fma_peak)", "fp64_peak_tflops": f64,
+                "launch_ms": ms_per_step, "algorithmic_flops_per_agent_step": flops,
+                "note": "pair loops run an fp32 filter pass + exact fp64 on the survivors; flops = SURVEY 8(d) count (selection excluded)",
+                "kernel": "swarm::k_step<PH=0, 1024 threads>"}
+
+    regimes = {}
+    sampler = ClockSampler(local_rank); sampler.start()
+    want = ["random", "converged"] if args.regime == "both" else [args.regime]
+    for regime in want:
+        if regime == "random":
+            sim.reset(seed=226, episode=0, env_offset=env0)              # assembly.py:156-223 on the device
+            for _ in range(EP):                                          # untimed pre-roll: one full cycle -> uniform episode ages
+                step_random()
+            ms, launches = timed(step_random, K, W)
+        else:
+            blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, "converged")
+            sim.set_grid(blocks, n_g, l_cell)
+            sim.set_state(p, dp)
+            sim.observe()
+            sim.step(acts[0])                                            # produces the first prior action
+            for _ in range(20):
+                step_converged()
+            ms, launches = timed(step_converged, K, W)
+        stats = all_reduce_stats(episode_stats(sim.reward, sim.in_flags)).tolist()   # episode statistics (not timed)
+        regimes[regime] = {"ms_per_step": ms / K, "value": world * E * n_a * K / (ms * 1e-3), "gpu_launches": int(launches),
+                           "roofline": roofline_of(ms / K),
+                           "mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]}
+    clocks = sampler.stop()
+    head = regimes[want[0]]
+    ms, launches, value, roofline = head["ms_per_step"] * K, head["gpu_launches"], head["value"], head["roofline"]
+    bytes_per_launch = sim.algorithmic_bytes_per_agent_step(survey=True) * E * n_a
     prof = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.isfile(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{args.layout}_{args.regime}_bytes_per_launch")
+            roofline["traffic"] = json.load(open(prof)).get(f"{args.layout}_{want[0]}_bytes_per_launch")
         except Exception:
             pass
 
     # ---- end to end through host buffers ----
     e2e = None
     if not args.no_e2e:
+        sim.reset(seed=226, episode=0, env_offset=env0)                  # the e2e loop runs from the reference's reset distribution
         osz = 8 if parity else 4
         act_h = torch.empty(ring, E, 2, n_a, dtype=torch.float32).pin_memory()
         act_h.copy_(acts.cpu())
@@ -382,9 +433,22 @@ def main():
         barrier()
         ems = e0.elapsed_time(e1)
         ems = max_over_ranks(ems, device="cuda")
+        # what the host side can take: a plain pinned D2H copy of the same observation buffer, all ranks at once (no kernels)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            obs_h.copy_(sim.obs, non_blocking=True)
+        c1.record()
+        barrier()
+        cms = max_over_ranks(c0.elapsed_time(c1), device="cuda") / 5
+        d2h = E * n_a * (sim.obs_dim + 1 + 2) * osz
         e2e = {"value": world * E * n_a * K / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": E * 2 * n_a * 4, "d2h_bytes_per_step": E * n_a * (sim.obs_dim + 1 + 2) * osz,
-               "ms_per_step": ems / K, "api": "swarm_step_host (C ABI, pinned host buffers)"}
+               "h2d_bytes_per_step": E * 2 * n_a * 4, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ems / K, "api": "swarm_step_host (C ABI, pinned host buffers)",
+               "achieved_d2h_gbs_per_rank": d2h / (ems / K * 1e-3) / 1e9,
+               "host_copy_ceiling_gbs_per_rank": obs_h.numel() * osz / (cms * 1e-3) / 1e9,
+               "host_copy_ceiling_note": f"plain cudaMemcpyAsync D2H of the obs buffer into pinned memory, {world} rank(s) concurrently"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
     cpu = None
@@ -418,12 +482,13 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"assembly env, {n_a} agents x {E} envs per GPU, env-sharded (BASELINE config 3)" if n_a == 30 else
                                     f"large swarm: {n_a} agents x {E} envs per GPU (BASELINE config 4)"),
-                       "n_a": n_a, "envs_per_gpu": E, "layout": args.layout, "regime": args.regime,
+                       "n_a": n_a, "envs_per_gpu": E, "layout": args.layout, "regime": want[0],
+                       "episodes": f"{EP}-step episodes, env e auto-resets (swarm_reset_envs) when t = e mod {EP}; the reset launches are inside the timed region, reset envs are not counted as extra agent-steps",
                        "out_dtype": "f64" if parity else "f32", "state_dtype": "f64",
                        "grid_scan": "all-pairs" if args.brute_force_scan else "word-box culled",
                        "l2": f"working set per step {bytes_per_launch / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                        "actions": f"ring of {ring} pre-generated device buffers"},
-            "last_step_stats": {"mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]},
+            "regimes": regimes,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "widened_path": extras,
         }

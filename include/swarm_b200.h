@@ -164,9 +164,20 @@ int swarm_set_shapes(swarm_sim *sim, int32_t n_shapes, const double *grids, cons
  * those with env_mask[e] != 0; device pointer or NULL), then the observation of the new state (ENV:221).  Random draws come
  * from a counter-based generator keyed by (seed, episode, env_offset + e), not from NumPy's global stream; the map from the
  * draws to grid_center / p / dp is the reference's.  info_dev (device, [E][8] f64, may be NULL) receives per env
- * {shape index, cos, sin, offset_x, offset_y, wide-spawn flag, 0, 0}. */
+ * {shape index, cos, sin, offset_x, offset_y, wide-spawn flag, cluster_centre_x, cluster_centre_y}.  Draw k of env e is
+ * u = (mix64(seed, episode, env_offset + e, k) >> 11) * 2^-53 (see k_reset); agent i uses draws 16 + i, 16 + n_a + i (position)
+ * and 16 + 2 n_a + i, 16 + 3 n_a + i (velocity), so a host can rebuild p / dp exactly. */
 int swarm_reset(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
                 double *info_dev, void *stream);
+
+/* The same reset for a LIST of envs (device int32 array of `count` distinct env ids): only those envs are re-randomised and
+ * re-observed, one CTA each — the auto-reset of a vector env whose episodes end at different steps (ENV:156-223 per env). */
+int swarm_reset_envs(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t env_offset, const int32_t *env_list_dev,
+                     int32_t count, double *info_dev, void *stream);
+
+/* Measurement aid (bench.py): dense FMA throughput of `device` in TFLOP/s, fp32 and fp64, from a register-resident FMA loop —
+ * the roofline denominator of the O(n_a^2) large-swarm configuration. */
+int swarm_measure_fma_peak(int32_t device, double *fp32_tflops, double *fp64_tflops);
 
 /* Evaluation metrics of the reference wrapper for every env, on the device: out_dev [E][3] f64 =
  * {coverage_rate, distribution_uniformity, voronoi_based_uniformity} (assembly_wrapper.py:48-72, 74-101, 103-129). */
@@ -190,6 +201,13 @@ int swarm_set_obs_buffer(swarm_sim *sim, void *obs_dev);
 /* Tell the handle that the caller overwrote p / dp (device buffers) outside step(): the next step recomputes the
  * prior from the new state and the stale neighbor_index, exactly like the reference would (ENV:613-624). */
 int swarm_mark_state_dirty(swarm_sim *sim);
+
+/* State restore (checkpoint / handle rebuilt with a larger n_g_max): the caller copied neighbor_index, in_flags and
+ * nearest_cell (and whatever outputs it wants to keep) of an earlier observation into this handle's buffers; the handle
+ * treats them as its last observation, so swarm_step is legal and computes its prior from that neighbour list
+ * (ENV:613-624 uses the neighbor_index of the last _get_obs call).  swarm_is_observed: 1 once an observation exists. */
+int swarm_restore_observation(swarm_sim *sim);
+int swarm_is_observed(const swarm_sim *sim);
 
 /* reset() tail, ENV:221 -> _get_obs: observation (+ reward) of the current state, no dynamics. */
 int swarm_observe(swarm_sim *sim, void *stream);

@@ -10,7 +10,7 @@ so that marl_llm/train/train_assembly.py and eval/eval_assembly.py see the env t
     env.p, env.dp, env.env.grid_center = ...            # readable and writable (eval_assembly.py:34-57,137-151)
 
 `num_envs > 1` gives a vectorised variant with a leading batch axis on every array (not in the reference).
-All arithmetic runs in the sm_100a kernels (marl_llm_b200/csrc); there is no CPU fallback.  render() is out of scope.
+All arithmetic runs in the sm_100a kernels (marl_llm_b200/csrc); there is no CPU fallback.  render() is a no-op.
 """
 import pickle
 
@@ -118,9 +118,19 @@ class AssemblySwarmEnv:
         grids = [self._grid_center] if E == 1 else list(self._grid_center)
         n_g = max(g.shape[1] for g in grids)
         if n_g > self._n_g_cap:                                          # eval may install a bigger shape
-            p, dp = self.p, self.dp
+            # The handle is rebuilt with a larger cell capacity.  Everything the next step() reads from the last observation
+            # moves over (eval_assembly.py:34-57 swaps the shape mid-episode, with no reset): p / dp, the neighbour list the
+            # prior is computed from (ENV:613-624), in_flags, the outputs; the new handle is then marked as observed.
+            old = self._sim
+            keep = {k: getattr(old, k).clone() for k in ("p", "dp", "neighbor_index", "in_flags", "nearest_cell", "obs", "reward",
+                                                         "sensed_index", "occupied_index")}
+            observed = old.observed
             self._make_sim(n_g)
-            self._sim.set_state(np.reshape(p, (E, 2, self.n_a)), np.reshape(dp, (E, 2, self.n_a)))
+            for k, v in keep.items():
+                getattr(self._sim, k).copy_(v)
+            if observed:
+                self._sim.restore_observation()
+            self._sim.mark_state_dirty()
         blocks, ng = self._sim.pack_grids(grids, self._n_g_cap)
         l_cell = np.broadcast_to(np.asarray(self._l_cell, dtype=np.float64), (E,))
         self._sim.set_grid(blocks, ng, l_cell)
@@ -246,7 +256,9 @@ class AssemblySwarmEnv:
         return self._host(obs), self._host(rew), self._host(done), info, last
 
     def render(self, mode="human"):
-        raise NotImplementedError("rendering (matplotlib, ENV:668-747) is outside the step() hot path")
+        """ENV:668-747 draws the swarm with matplotlib; drawing is outside the step() hot path, so this is a no-op that keeps
+        train_assembly.py:93-94 and eval_assembly.py:147 running unchanged (they ignore the return value)."""
+        return None
 
     def close(self):
         if self._sim is not None:

@@ -177,7 +177,7 @@ class BatchedAssemblySim:
 
     def reset(self, seed, episode=0, env_offset=0, env_mask=None):
         """reset() of assembly.py:156-223 for all envs (or those where env_mask is True) on the device, then the first
-        observation.  Returns obs; `self.reset_info` [E, 8] holds {shape, cos, sin, off_x, off_y, wide-spawn flag, 0, 0}."""
+        observation.  Returns obs; `self.reset_info` [E, 8] holds {shape, cos, sin, off_x, off_y, wide-spawn flag, cluster_x, cluster_y}."""
         if not hasattr(self, "reset_info"):
             self.reset_info = torch.zeros(self.E, 8, dtype=torch.float64, device=self.device)
         mptr = None
@@ -188,6 +188,21 @@ class BatchedAssemblySim:
         check(self.lib.swarm_reset(self._h, int(seed), int(episode), int(env_offset), mptr,
                                    C.c_void_p(self.reset_info.data_ptr()), self._stream()), "swarm_reset")
         return self.obs
+
+    def reset_envs(self, env_ids, seed, episode=0, env_offset=0):
+        """reset() for the listed envs only (int32 CUDA tensor of distinct env ids): the auto-reset of a vector env."""
+        assert env_ids.is_cuda and env_ids.dtype == torch.int32 and env_ids.is_contiguous()
+        if not hasattr(self, "reset_info"):
+            self.reset_info = torch.zeros(self.E, 8, dtype=torch.float64, device=self.device)
+        check(self.lib.swarm_reset_envs(self._h, int(seed), int(episode), int(env_offset), C.c_void_p(env_ids.data_ptr()),
+                                        int(env_ids.numel()), C.c_void_p(self.reset_info.data_ptr()), self._stream()), "swarm_reset_envs")
+        return self.obs
+
+    def measure_fma_peak(self):
+        """(fp32, fp64) dense FMA TFLOP/s of this device, measured by a register-resident FMA loop."""
+        a, b = C.c_double(), C.c_double()
+        check(self.lib.swarm_measure_fma_peak(self.device.index, C.byref(a), C.byref(b)), "swarm_measure_fma_peak")
+        return a.value, b.value
 
     def metrics(self):
         """[E, 3] float64 device tensor: coverage_rate, distribution_uniformity, voronoi_based_uniformity of every env
@@ -230,6 +245,16 @@ class BatchedAssemblySim:
 
     def mark_state_dirty(self):
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
+
+    @property
+    def observed(self):
+        """True once an observation exists (observe / reset / restore_observation): step() needs its neighbour list."""
+        return bool(self.lib.swarm_is_observed(self._h))
+
+    def restore_observation(self):
+        """State restore: the caller copied neighbor_index / in_flags / nearest_cell (and the outputs) of an earlier handle
+        into this one's buffers; treat them as this handle's last observation (the next step computes its prior from them)."""
+        check(self.lib.swarm_restore_observation(self._h), "swarm_restore_observation")
 
     # ------------------------------------------------------------------------------------------------
     def observe(self):
@@ -290,18 +315,25 @@ class BatchedAssemblySim:
         return dict(threads_per_cta=t.value, smem_bytes=s.value, ctas=c.value)
 
     # ------------------------------------------------------------------------------------------------
-    def algorithmic_bytes_per_agent_step(self, mean_n_g=None):
-        """Unavoidable HBM traffic of one step per agent, for the roofline figure."""
+    def algorithmic_bytes_per_agent_step(self, mean_n_g=None, survey=True):
+        """Unavoidable HBM traffic of one step per agent, for the roofline figure.  survey=True is SURVEY.md §8(d)'s count
+        (read a, read + write p/dp, write obs, reward, done, a_prior, read the env's cells once: 1126 B for the production layout
+        at n_g = 512, n_a = 30; + the four index arrays in the parity layout).  survey=False adds what this implementation also
+        moves by design: neighbor_index / in_flags (the next prior reads them) and the nearest-cell seed."""
         osz = 4 if self.out_dtype == torch.float32 else 8
         ng = float(np.mean(self.n_g)) if mean_n_g is None else mean_n_g
         b = 2 * 4                      # read action (f32 x 2)
         b += 4 * 8 + 4 * 8             # read + write p, dp
         b += self.obs_dim * osz        # write obs
-        b += osz                       # write reward
-        b += (2 * osz if self.want_prior else 0)       # write next prior
-        b += TOPO_NEI_MAX * 4 + 4      # write neighbor_index + in_flags
-        b += 4 + 4                     # read + write nearest_cell (seed of the nearest-cell search)
-        b += 2 * 8 * math.ceil(ng / 32) * 32 / self.n_a   # read the env's cell list once per env
+        b += osz + 1                   # write reward, done
+        b += 2 * osz                   # write a_prior
+        b += 2 * 8 * ng / self.n_a     # read the env's cell list once per env
         if self.emit_indices:
-            b += (NUM_OBS_GRID_MAX + NUM_OCC_GRID_MAX) * 4
+            b += (TOPO_NEI_MAX + 1 + NUM_OBS_GRID_MAX + NUM_OCC_GRID_MAX) * 4
+        if not survey:
+            b -= 1                     # done is constant False and never rewritten
+            if not self.emit_indices:
+                b += TOPO_NEI_MAX * 4 + 4
+            b += 4 + 4                 # read + write nearest_cell (seed of the nearest-cell search)
+            b += 2 * 8 * (math.ceil(ng / 32) * 32 - ng) / self.n_a
         return b

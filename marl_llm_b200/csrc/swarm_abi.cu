@@ -136,6 +136,9 @@ struct swarm_sim {
 
 extern "C" {
 
+static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, cudaStream_t st, const int32_t *env_list = nullptr,
+                       int32_t count = 0);
+
 /* shared with the other translation units of the library */
 int swarm_set_last_error_(int code, const char *msg) { return fail(code, msg); }
 
@@ -294,13 +297,70 @@ int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offs
     R.shape_grid = s->d_shape_grid; R.shape_n_g = s->d_shape_ng; R.shape_thresh = s->d_shape_thr;
     R.p = s->buf.p; R.dp = s->buf.dp; R.grid = reinterpret_cast<double2 *>(s->buf.grid); R.n_g = s->buf.n_g;
     R.in_thresh = s->buf.in_thresh; R.wbox = reinterpret_cast<float4 *>(s->buf.word_box); R.frame = s->buf.frame;
-    R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = env_mask;
+    R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = env_mask; R.env_list = nullptr;
     R.seed = seed; R.episode = episode; R.env_offset = env_offset;
     k_reset<<<s->cfg.num_envs, 128, 0, (cudaStream_t)stream>>>(R);
     CU_TRY(cudaGetLastError());
     s->launches++;
     s->prior_dirty = true;
     return swarm_observe(s, stream);     // ENV:221; a masked reset re-observes every env (idempotent for the untouched ones)
+}
+
+/* swarm_reset for a LIST of envs (device int32 array, no duplicates): only those envs are re-randomised and re-observed,
+ * one CTA each — the auto-reset of a vector env whose episodes end at different steps. */
+int swarm_reset_envs(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offset, const int32_t *env_list_dev, int32_t count,
+                     double *info_dev, void *stream) {
+    if (!s || !env_list_dev) return fail(SWARM_ERR_INVALID, "null argument");
+    if (count <= 0 || count > s->cfg.num_envs) return fail(SWARM_ERR_INVALID, "count out of range");
+    if (s->n_shapes <= 0) return fail(SWARM_ERR_INVALID, "swarm_reset_envs before swarm_set_shapes");
+    if (!s->observed) return fail(SWARM_ERR_INVALID, "swarm_reset_envs needs a full reset / observe first");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    ResetParams R;
+    R.n_a = s->cfg.n_a; R.n_g_pad = s->K.n_g_pad; R.n_g_cap = s->cfg.n_g_max; R.n_shapes = s->n_shapes;
+    R.half_w = s->K.half_w; R.half_h = s->K.half_h;
+    R.shape_grid = s->d_shape_grid; R.shape_n_g = s->d_shape_ng; R.shape_thresh = s->d_shape_thr;
+    R.p = s->buf.p; R.dp = s->buf.dp; R.grid = reinterpret_cast<double2 *>(s->buf.grid); R.n_g = s->buf.n_g;
+    R.in_thresh = s->buf.in_thresh; R.wbox = reinterpret_cast<float4 *>(s->buf.word_box); R.frame = s->buf.frame;
+    R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = nullptr; R.env_list = env_list_dev;
+    R.seed = seed; R.episode = episode; R.env_offset = env_offset;
+    k_reset<<<count, 128, 0, (cudaStream_t)stream>>>(R);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    // observation + prior of the new state for the listed envs only; the others keep theirs (the a_prior buffer written is the
+    // one holding the prior of the CURRENT state, which the next step returns)
+    return launch_step(s, false, nullptr, SWARM_F32, (cudaStream_t)stream, env_list_dev, count);
+}
+
+/* measurement aid: dense FMA throughput of this device (TFLOP/s), fp32 and fp64 — the roofline denominator of the O(n_a^2)
+ * configuration; best of 3 timed launches each */
+int swarm_measure_fma_peak(int32_t device, double *fp32_tflops, double *fp64_tflops) {
+    if (!fp32_tflops || !fp64_tflops) return fail(SWARM_ERR_INVALID, "null argument");
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    void *sink = nullptr;
+    CU_TRY(cudaMalloc(&sink, 64));
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a)); CU_TRY(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best[2] = {0.0, 0.0};
+    for (int which = 0; which < 2; ++which) {
+        const int iters = which ? 1 << 14 : 1 << 17;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU_TRY(cudaEventRecord(a));
+            if (which) k_fma_peak<double><<<blocks, threads>>>(iters, (double *)sink);
+            else k_fma_peak<float><<<blocks, threads>>>(iters, (float *)sink);
+            CU_TRY(cudaEventRecord(b));
+            CU_TRY(cudaEventSynchronize(b));
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, a, b));
+            const double tf = (double)blocks * threads * (double)iters * 16.0 / (ms * 1e-3) / 1e12;
+            if (rep > 0 && tf > best[which]) best[which] = tf;
+        }
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    *fp32_tflops = best[0]; *fp64_tflops = best[1];
+    return SWARM_OK;
 }
 
 int swarm_metrics(swarm_sim *s, double *out_dev, void *stream) {
@@ -345,17 +405,28 @@ int swarm_mark_state_dirty(swarm_sim *s) {
     return SWARM_OK;
 }
 
-static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, cudaStream_t st) {
+int swarm_restore_observation(swarm_sim *s) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    s->observed = true;
+    s->prior_dirty = true;       // the prior of the restored state is computed by k_prior at the next step (ENV:613-624)
+    return SWARM_OK;
+}
+
+int swarm_is_observed(const swarm_sim *s) { return (s && s->observed) ? 1 : 0; }
+
+static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, cudaStream_t st, const int32_t *env_list, int32_t count) {
     KParams K = s->K;
     K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
     K.prior_next = s->buf.a_prior[dyn ? (1 - s->pending) : s->pending];
+    K.env_list = env_list;
+    const int ctas = env_list ? count : s->cfg.num_envs;
     const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
     if (s->split) {
-        pick_step(f32, dyn, emit, s->nt, 1)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
-        pick_step(f32, dyn, emit, s->nt, 2)<<<s->cfg.num_envs, s->nt, s->smem2, st>>>(K);
+        pick_step(f32, dyn, emit, s->nt, 1)<<<ctas, s->nt, s->smem, st>>>(K);
+        pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
         s->launches += 2;
     } else {
-        pick_step(f32, dyn, emit, s->nt, 0)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+        pick_step(f32, dyn, emit, s->nt, 0)<<<ctas, s->nt, s->smem, st>>>(K);
         s->launches++;
     }
     CU_TRY(cudaGetLastError());

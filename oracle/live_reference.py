@@ -101,10 +101,10 @@ def import_reference_gym():
 
 
 def default_args(n_a=30, results_file=None, training_method="llm_rl", agent_strategy="input",
-                 is_boundary=True, is_collected=False):
+                 is_boundary=True, is_collected=False, is_con_self_state=True):
     """Namespace with the fields assembly.py:93-112 reads; defaults from assembly_cfg.py:152-166."""
     return argparse.Namespace(
-        n_a=n_a, is_boundary=is_boundary, is_con_self_state=True, is_feature_norm=False,
+        n_a=n_a, is_boundary=is_boundary, is_con_self_state=is_con_self_state, is_feature_norm=False,
         dynamics_mode="Cartesian", render_traj=False, traj_len=15, agent_strategy=agent_strategy,
         training_method=training_method, is_collected=is_collected,
         results_file=results_file or write_results_pkl(), video=False)

@@ -152,3 +152,16 @@ def fill_actions(E, n_a, seed, step, env0=0):
     act = np.empty((E, 2, n_a), dtype=np.float32)
     lib().orc_fill_actions(C.c_int(E), C.c_int(n_a), C.c_uint64(seed), C.c_uint64(step), C.c_uint64(env0), _fp(act))
     return act
+
+
+def reset_uniform(seed, episode, env, k):
+    """The k-th U[0,1) draw of env `env` in swarm_reset's counter-based generator (marl_llm_b200/csrc/swarm_kernels.cuh: mix64 /
+    u01), restated with NumPy uint64 arithmetic; env and k broadcast.  Lets a test rebuild the reset state from the draws."""
+    with np.errstate(over="ignore"):
+        u = np.uint64
+        z = (u(seed) * u(0x9E3779B97F4A7C15) + u(episode) * u(0xBF58476D1CE4E5B9)
+             + np.asarray(env, dtype=np.uint64) * u(0x94D049BB133111EB) + np.asarray(k, dtype=np.uint64) * u(0xD6E8FEB86659FD93))
+        z = z ^ (z >> u(30)); z = z * u(0xBF58476D1CE4E5B9)
+        z = z ^ (z >> u(27)); z = z * u(0x94D049BB133111EB)
+        z = z ^ (z >> u(31))
+    return (z >> u(11)).astype(np.float64) * (1.0 / 9007199254740992.0)

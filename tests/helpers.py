@@ -14,10 +14,10 @@ def load_shapes():
                 grid_origin=[np.ascontiguousarray(z["grid_coords"][k, :n_g[k]].T) for k in range(len(n_g))])
 
 
-def goal_seeking_action(obs, dp, rng, noise=0.3):
-    """Noisy PD controller towards the target cell (obs rows 28:30 = target - p): drives agents into
-    the shape so the in-shape / occupancy / subsample / reward branches are exercised."""
-    a = 3.0 * obs[..., 28:30, :] - 1.0 * dp + rng.normal(0, noise, dp.shape)
+def goal_seeking_action(obs, dp, rng, noise=0.3, target_row=28):
+    """Noisy PD controller towards the target cell (obs rows 28:30 = target - p; 24:26 without the self-state column): drives
+    agents into the shape so the in-shape / occupancy / subsample / reward branches are exercised."""
+    a = 3.0 * obs[..., target_row:target_row + 2, :] - 1.0 * dp + rng.normal(0, noise, dp.shape)
     return np.clip(a, -1, 1).astype(np.float32)
 
 

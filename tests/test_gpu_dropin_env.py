@@ -214,3 +214,67 @@ def test_dropin_env_runs_its_own_rule_strategy_like_collect_expert_data():
         inside.append(float(np.mean(np.all(obs[28:30] == 0, axis=0))))       # target offset is zero iff in the shape (CPP:136-137)
     # the reference with the same seed: in-shape fraction 0.45 over the first 20 steps, 1.0 over the last 20
     assert np.mean(inside[:20]) < 0.7 and np.mean(inside[-20:]) > 0.95
+
+
+@pytest.mark.gpu
+def test_device_metrics_match_values_recorded_from_the_real_wrapper():
+    """(f2) swarm_metrics / k_metrics against the numbers the UNMODIFIED AssemblySwarmWrapper produced (assembly_wrapper.py:48-129;
+    tests/golden/metrics.npz, recorded by tests/golden/make_metric_goldens.py): coverage exact, the two variance ratios to
+    1e-12 (NumPy's np.var sums pairwise, the kernel sequentially)."""
+    import torch
+    from marl_llm_b200.batched import BatchedAssemblySim
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "metrics.npz"))
+    for k in range(int(z["n_cases"])):
+        grid, r, P, want = z[f"c{k}_grid"], float(z[f"c{k}_r_avoid"]), z[f"c{k}_p"], z[f"c{k}_metrics"]
+        K, _, n_a = P.shape
+        sim = BatchedAssemblySim(K, n_a, grid.shape[1], r, out_dtype=torch.float64)
+        blocks, n_g = sim.pack_grids([grid] * K, grid.shape[1])
+        sim.set_grid(blocks, n_g, [float(z[f"c{k}_l_cell"])] * K)
+        sim.set_state(P, np.zeros_like(P))
+        got = sim.metrics().cpu().numpy()
+        assert np.array_equal(got[:, 0], want[:, 0]), k
+        assert np.allclose(got[:, 1:], want[:, 1:], rtol=1e-12, atol=0), (k, np.abs(got[:, 1:] - want[:, 1:]).max())
+        assert want[:, 0].max() > 0.3
+
+
+@pytest.mark.gpu
+def test_installing_a_larger_shape_between_steps_keeps_the_last_observation(gym):
+    """eval_assembly.py:34-57 swaps the target shape mid-episode with no reset.  When the new shape has more cells than the
+    handle was sized for, the drop-in rebuilds the handle; the next step must still use the LAST observation's neighbour
+    list for its prior (assembly.py:613-624) and the new grid for everything else — compared with the oracle."""
+    from oracle import oracle as orc
+    sh = load_shapes()
+    n_a = 30
+    blob = results_blob()
+    order = np.argsort(sh["n_g"])
+    small = [int(k) for k in order[:3]]                       # the env only knows the three smallest shapes ...
+    blob = {key: [val[k] for k in small] for key, val in blob.items()}
+    env = gym.wrappers.AssemblySwarmWrapper(gym.make("AssemblySwarm-v0").unwrapped, make_args(n_a, results_file=blob))
+    np.random.seed(4)
+    env.reset()
+    cap0 = env.env._n_g_cap
+    rng = np.random.RandomState(1)
+    for t in range(10):
+        if t == 4:                                            # ... and the caller installs the largest one
+            k = int(order[-1])
+            assert sh["n_g"][k] > cap0
+            env.env.l_cell = float(sh["l_cell"][k])
+            env.env.grid_center_origin = sh["grid_origin"][k]
+            env.env.n_g = sh["grid_origin"][k].shape[1]
+            env.env.grid_center = sh["grid_origin"][k].copy() + np.array([[0.3], [-0.2]])
+        p0, dp0, nbr0 = env.p.copy(), env.dp.copy(), env.env.neighbor_index.copy()
+        a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32)
+        obs, rew, done, info, prior = env.step(a)
+        grid = env.env.grid_center
+        P = orc.make_params(n_a, grid.shape[1], float(env.env.l_cell), env.r_avoid)
+        ob = orc.OracleBatch([P])
+        ob.p[0], ob.dp[0] = p0, dp0
+        ob.set_grid(0, grid)
+        ob.neighbor_index[0] = nbr0
+        ob.step(a[None])
+        assert np.array_equal(obs, ob.obs[0]) and np.array_equal(prior, ob.a_prior[0]) and np.array_equal(rew, ob.reward[0]), t
+        assert np.array_equal(env.p, ob.p[0]) and np.array_equal(env.env.neighbor_index, ob.neighbor_index[0])
+    assert env.env._n_g_cap > cap0
+    env.render()                                              # a no-op on the drop-in (train_assembly.py:93-94, eval_assembly.py:147)
+    env.close()

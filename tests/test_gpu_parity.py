@@ -49,14 +49,14 @@ def test_golden_trajectories_bit_exact(case):
     assert not sim.done.any()
 
 
-def build_batch(E, n_a, seed, shapes=None, shape_of=None):
+def build_batch(E, n_a, seed, shapes=None, shape_of=None, **param_kw):
     shapes = shapes or load_shapes()
     rng = np.random.RandomState(seed)
     r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
     params, grids, P, DP = [], [], [], []
     for e in range(E):
         k, grid, p, dp = reset_like_reference(rng, n_a, shapes)
-        params.append(orc.make_params(n_a, grid.shape[1], float(shapes["l_cell"][k]), r_avoid))
+        params.append(orc.make_params(n_a, grid.shape[1], float(shapes["l_cell"][k]), r_avoid, **param_kw))
         grids.append(grid); P.append(p); DP.append(dp)
     return shapes, r_avoid, params, grids, np.stack(P), np.stack(DP)
 
@@ -114,6 +114,79 @@ def test_batch_vs_oracle_every_step(n_a, E, steps, mode):
     if mode != "random" and n_a >= 7:
         assert in_shape > 0
     assert not sim.done.any()
+
+
+@pytest.mark.parametrize("n_a,E,emit", [(30, 96, True), (30, 96, False), (31, 32, True), (7, 48, True), (7, 48, False), (100, 8, True)])
+def test_without_self_state_obs_dim_188(n_a, E, emit):
+    """is_con_self_state=False (assembly.py:105-108, 801; AssemblyEnv.cpp:103-126): obs_dim 188, the own-state rows are
+    dropped and the first sensed-cell row is 28 instead of 32.  Both layouts (parity: fp64 + index arrays; production: fp32),
+    >= 100 steps with goal-seeking envs so the in-shape / occupancy / subsample branches fire; the observation buffer is
+    poisoned before every step.  The oracle is pinned to the live reference for this flag (tests/test_oracle_vs_reference.py)."""
+    steps = 120
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=300 + n_a, is_con_self_state=False)
+    ngm = int(shapes["n_g"].max())
+    dt = torch.float64 if emit else torch.float32
+    cast = np.float64 if emit else np.float32
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit, is_con_self_state=False)
+    assert sim.obs_dim == 188 and sim.obs.shape == (E, 188, n_a)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.obs.fill_(float("nan"))
+    sim.observe(); ob.observe(with_reward=True)
+    assert np.array_equal(sim.obs.cpu().numpy(), ob.obs.astype(cast))
+    rng = np.random.RandomState(17)
+    in_shape = sub = 0
+    for t in range(steps):
+        a_goal = goal_seeking_action(ob.obs, ob.dp, rng, target_row=24)
+        a = np.where((np.arange(E) % 4 != 0)[:, None, None], a_goal, rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32))
+        sim.obs.fill_(float("nan"))
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        if emit:
+            compare_all(sim, ob, t)
+        else:
+            for name, got, ref in (("p", sim.p, ob.p), ("dp", sim.dp, ob.dp), ("obs", sim.obs, ob.obs.astype(cast)),
+                                   ("reward", sim.reward, ob.reward.astype(cast)), ("a_prior", sim.a_prior, ob.a_prior.astype(cast)),
+                                   ("nbr", sim.neighbor_index, ob.neighbor_index), ("in_flags", sim.in_flags, ob.in_flags)):
+                assert np.array_equal(got.cpu().numpy(), ref), (name, t)
+        in_shape += int(ob.in_flags.sum()); sub += int(((ob.sensed_index >= 0).sum(2) == 80).sum())
+    assert in_shape > 100 and ob.reward.sum() >= 0
+    if n_a >= 30:
+        assert sub > 0                                          # the 80-cell subsample branch ran
+
+
+@pytest.mark.parametrize("self_state,emit", [(True, True), (True, False), (False, True)])
+def test_without_prior_training_method_not_llm_rl(self_state, emit):
+    """want_prior=False (training_method != 'llm_rl': assembly.py:605, 666): step() returns None as its 5th output and the
+    a_prior buffers are never written (they keep a sentinel); everything else equals the oracle every step."""
+    E, n_a, steps = 64, 30, 110
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=41, is_con_self_state=self_state, want_prior=False)
+    ngm = int(shapes["n_g"].max())
+    dt = torch.float64 if emit else torch.float32
+    cast = np.float64 if emit else np.float32
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit, is_con_self_state=self_state, want_prior=False)
+    for b in sim._a_prior:
+        b.fill_(-123.0)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe(with_reward=True)
+    rng = np.random.RandomState(19)
+    l0 = sim.launch_count
+    for t in range(steps):
+        a = goal_seeking_action(ob.obs, ob.dp, rng, target_row=28 if self_state else 24)
+        out = sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        assert out[4] is None
+        if t == 50:                                             # a state poke must not resurrect the stand-alone prior kernel
+            sim.set_state(ob.p, ob.dp)
+        fields = ("p", "dp", "obs", "reward", "nbr", "in_flags") + (("sensed", "occupied") if emit else ())
+        got = sim_snapshot(sim)
+        ref = dict(p=ob.p, dp=ob.dp, obs=ob.obs.astype(cast), reward=ob.reward.astype(cast), nbr=ob.neighbor_index,
+                   in_flags=ob.in_flags, sensed=ob.sensed_index, occupied=ob.occupied_index)
+        for k in fields:
+            assert np.array_equal(got[k], ref[k]), (k, t)
+    assert ob.in_flags.sum() > 0 and not ob.a_prior.any()
+    assert sim.launch_count - l0 == 2 * steps                   # two launches per step, no k_prior launch
+    for b in sim._a_prior:
+        assert bool((b == -123.0).all())
 
 
 def test_config2_4096_envs_200_steps():

@@ -55,6 +55,16 @@ def test_reset_state_is_the_reference_map_of_the_draws_and_rollout_matches_oracl
     wide = info[:, 5] > 0
     assert wide.any() and (~wide).any()
     assert (np.ptp(p[~wide], axis=2) <= 2.0).all()            # clustered spawn: U(-1,1) around a centre (assembly.py:207)
+    # p / dp rebuilt exactly from the generator's draws with the reference's map (assembly.py:202-208, 215)
+    env_id, ia = np.arange(E)[:, None], np.arange(n_a)[None, :]
+    ux, uy = orc.reset_uniform(226, 0, env_id, 16 + ia), orc.reset_uniform(226, 0, env_id, 16 + n_a + ia)
+    px = np.where(wide[:, None], -2.4 + 2.0 * 2.4 * ux, (-1.0 + 2.0 * ux) + info[:, 6:7])
+    py = np.where(wide[:, None], -2.4 + 2.0 * 2.4 * uy, (-1.0 + 2.0 * uy) + info[:, 7:8])
+    assert np.array_equal(p[:, 0], px) and np.array_equal(p[:, 1], py)
+    assert np.array_equal(dp[:, 0], -0.5 + orc.reset_uniform(226, 0, env_id, 16 + 2 * n_a + ia))
+    assert np.array_equal(dp[:, 1], -0.5 + orc.reset_uniform(226, 0, env_id, 16 + 3 * n_a + ia))
+    assert np.array_equal(info[:, 0], np.minimum((orc.reset_uniform(226, 0, np.arange(E), 0) * 7).astype(int), 6))   # randint(0, 7)
+    assert np.array_equal(info[:, 3], (-2.4 + 1.0) + (2.0 * 2.4 - 2.0) * orc.reset_uniform(226, 0, np.arange(E), 2))
     # the oracle, started from the same state, must agree on the first observation and on a rollout
     params = [orc.make_params(n_a, grids[e].shape[1], float(shapes["l_cell"][k[e]]), r_avoid) for e in range(E)]
     ob = orc.OracleBatch(params, nthreads=8, ng_max=ngm)

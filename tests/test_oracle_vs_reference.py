@@ -14,12 +14,14 @@ pytestmark = [pytest.mark.reference,
 FIELDS = ("p", "dp", "obs", "rew", "prior", "nbr", "inf", "sen", "occ")
 
 
-def rollout_pair(n_a, seed, mode, steps):
-    env = lr.make_env(n_a)
+def rollout_pair(n_a, seed, mode, steps, self_state=True, training_method="llm_rl"):
+    env = lr.make_env(n_a, is_con_self_state=self_state, training_method=training_method)
     np.random.seed(seed)
     env.reset()
     e = env.env
-    P = orc.make_params(n_a, e.n_g, float(e.l_cell), float(e.r_avoid))
+    want_prior = training_method == "llm_rl"
+    P = orc.make_params(n_a, e.n_g, float(e.l_cell), float(e.r_avoid), is_con_self_state=self_state, want_prior=want_prior)
+    assert e.obs.shape == (P.obs_dim, n_a) and P.obs_dim == (192 if self_state else 188)
     ob = orc.OracleBatch([P])
     ob.p[0], ob.dp[0] = e.p, e.dp
     ob.set_grid(0, e.grid_center)
@@ -33,9 +35,12 @@ def rollout_pair(n_a, seed, mode, steps):
         if mode == "random":
             a = rng.uniform(-1, 1, (2, n_a)).astype(np.float32)
         else:
-            a = goal_seeking_action(e.obs, e.dp, rng)
+            a = goal_seeking_action(e.obs, e.dp, rng, target_row=28 if self_state else 24)
         obs, rew, done, info, prior = env.step(a)
         ob.step(a[None])
+        if not want_prior:                                   # assembly.py:666: the 5th output is None unless llm_rl
+            assert prior is None and not ob.a_prior.any()
+            prior = ob.a_prior[0]
         got = dict(p=ob.p[0], dp=ob.dp[0], obs=ob.obs[0], rew=ob.reward[0], prior=ob.a_prior[0],
                    nbr=ob.neighbor_index[0], inf=ob.in_flags[0], sen=ob.sensed_index[0], occ=ob.occupied_index[0])
         ref = dict(p=e.p, dp=e.dp, obs=obs, rew=rew, prior=prior, nbr=e.neighbor_index, inf=e.in_flags,
@@ -64,6 +69,22 @@ def test_goal_seeking_exercises_in_shape_branches(seed):
 @pytest.mark.parametrize("n_a,steps", [(1, 20), (2, 50), (10, 100), (64, 60), (200, 10)])
 def test_other_swarm_sizes(n_a, steps):
     rollout_pair(n_a, 11 + n_a, "goal", steps)
+
+
+@pytest.mark.parametrize("n_a,seed,mode,steps", [(30, 21, "goal", 150), (31, 22, "goal", 100), (7, 23, "goal", 100), (30, 24, "random", 100)])
+def test_without_self_state_obs_dim_188(n_a, seed, mode, steps):
+    """is_con_self_state=False (assembly.py:105-108, 795-801; AssemblyEnv.cpp:103-126): the own-state column is dropped,
+    obs_dim = 188, every later row moves up by four."""
+    st = rollout_pair(n_a, seed, mode, steps, self_state=False)
+    if mode == "goal":
+        assert st["in_shape"] > 50 and st["occupied"] > 0, st
+
+
+@pytest.mark.parametrize("method,self_state", [("manual_rl", True), ("irl", False)])
+def test_without_prior_training_method_not_llm_rl(method, self_state):
+    """training_method != 'llm_rl' (assembly.py:605, 666): calculateActionPrior is never called, the 5th output is None."""
+    st = rollout_pair(30, 31, "goal", 120, self_state=self_state, training_method=method)
+    assert st["in_shape"] > 50, st
 
 
 def test_ref_glue_matches_the_real_env_class():
