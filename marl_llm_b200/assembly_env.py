@@ -105,6 +105,11 @@ class AssemblySwarmEnv:
             is_periodic=self.is_periodic, d_sen=self.d_sen, size_a=self.size_a, k_ball=float(self.k_ball),
             k_wall=float(self.k_wall), c_wall=float(self.c_wall), dt=self.dt, vel_max=self.Vel_max, mass=float(self.m_a),
             half_width=self.boundary_width_half, half_height=self.boundary_height_half)
+        # the shape library (ENV:116-119): grids installed by reset() / by the caller are recognised as rigid transforms of
+        # these shapes, which lets the simulator use its lookup-scan kernel (results are identical without it)
+        if n_g_cap >= max(self.n_gs):
+            self._sim.set_shapes([np.ascontiguousarray(np.asarray(g, dtype=np.float64).T) for g in self.grid_center_origins],
+                                 [float(v) for v in self.l_cells])
 
     # ---------------------------------------------------------------------------------------- helpers
     def _squeeze(self, a):

@@ -247,6 +247,11 @@ class BatchedAssemblySim:
         check(self.lib.swarm_mark_state_dirty(self._h), "swarm_mark_state_dirty")
 
     @property
+    def fast_path(self):
+        """True if the next step runs the lookup-scan kernel (shape library set, every env's grid recognised)."""
+        return bool(self.lib.swarm_fast_path(self._h))
+
+    @property
     def observed(self):
         """True once an observation exists (observe / reset / restore_observation): step() needs its neighbour list."""
         return bool(self.lib.swarm_is_observed(self._h))

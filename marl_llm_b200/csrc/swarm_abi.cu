@@ -48,9 +48,11 @@ double thresh_le(double h) {
 
 int round32(int n) { return (n + 31) & ~31; }
 
-size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0) {
+size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1) {
     (void)n_g_pad;
-    size_t b = (size_t)2 * CHUNK_CELLS * sizeof(double2) + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
+    size_t ring = (size_t)2 * CHUNK_CELLS * sizeof(double2);
+    if (rec_cap >= 0) ring = std::max(ring, (size_t)4 * rec_cap + 128);                            // lookup scan: row records + running counts
+    size_t b = ring + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
     if (phase != 2) {                                                                                // the second-half kernel parks its neighbour list on the idle ring
@@ -58,7 +60,7 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, i
         b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
     }
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
-    if (nt == 32 && n_words <= 32 && scratch > (size_t)2 * CHUNK_CELLS * sizeof(double2)) b += scratch;   // aliases the TMA ring when it fits
+    if (nt == 32 && n_words <= 32 && scratch > ring) b += scratch;   // aliases the TMA ring when it fits
     return b;
 }
 
@@ -69,6 +71,11 @@ template <typename OUT, int MAXT, int PH>
 step_fn_t pick2(bool dyn, bool emit) {
     if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, MAXT, PH> : (step_fn_t)k_step<OUT, true, false, MAXT, PH>;
     return emit ? (step_fn_t)k_step<OUT, false, true, MAXT, PH> : (step_fn_t)k_step<OUT, false, false, MAXT, PH>;
+}
+// second half with the lookup scan (single-warp envs whose grids all have a known pose)
+step_fn_t pick_fast(bool f32, bool emit) {
+    if (f32) return emit ? (step_fn_t)k_step<float, false, true, 128, 2, true> : (step_fn_t)k_step<float, false, false, 128, 2, true>;
+    return emit ? (step_fn_t)k_step<double, false, true, 128, 2, true> : (step_fn_t)k_step<double, false, false, 128, 2, true>;
 }
 step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt, int phase = 0) {
     if (nt <= 128) {
@@ -132,6 +139,12 @@ struct swarm_sim {
     float *d_act; size_t act_cap;          // step_host action staging
     double *d_shape_grid; int *d_shape_ng; double *d_shape_thr; int n_shapes;   // swarm_set_shapes
     std::vector<double> shape_l_cell;
+    // lookup scan: per-shape tables, per-env pose (library-owned device memory), host mirror of which envs are matched
+    ShapeTab *d_tabs; std::vector<void *> tab_allocs; std::vector<ShapeTab> h_tabs;
+    double4 *d_pose; int *d_shape_id;
+    std::vector<int> h_shape_id; long n_unposed;
+    bool fast_ok;           // the shapes / sizes allow the lookup kernel at all
+    int rec_cap; size_t smem_fast;
 };
 
 extern "C" {
@@ -210,6 +223,21 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
     s->d_stage = nullptr; s->stage_cap = 0; s->d_act = nullptr; s->act_cap = 0;
     s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
+    s->d_tabs = nullptr; s->d_pose = nullptr; s->d_shape_id = nullptr;
+    s->h_shape_id.assign(cfg->num_envs, -1); s->n_unposed = cfg->num_envs;
+    s->fast_ok = false; s->rec_cap = 0; s->smem_fast = 0;
+    {
+        cudaError_t e1 = cudaMalloc(&s->d_pose, sizeof(double4) * (size_t)cfg->num_envs);
+        cudaError_t e2 = cudaMalloc(&s->d_shape_id, sizeof(int) * (size_t)cfg->num_envs);
+        if (e1 == cudaSuccess && e2 == cudaSuccess) e1 = cudaMemset(s->d_shape_id, 0xFF, sizeof(int) * (size_t)cfg->num_envs);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            if (s->d_pose) cudaFree(s->d_pose);
+            if (s->d_shape_id) cudaFree(s->d_shape_id);
+            delete s;
+            return fail(SWARM_ERR_CUDA, "cudaMalloc of the pose arrays failed");
+        }
+    }
+    s->K.pose = s->d_pose; s->K.shape_id = s->d_shape_id;
     *out = s;
     return SWARM_OK;
 }
@@ -222,6 +250,10 @@ int swarm_destroy(swarm_sim *s) {
     if (s->d_shape_grid) cudaFree(s->d_shape_grid);
     if (s->d_shape_ng) cudaFree(s->d_shape_ng);
     if (s->d_shape_thr) cudaFree(s->d_shape_thr);
+    if (s->d_pose) cudaFree(s->d_pose);
+    if (s->d_shape_id) cudaFree(s->d_shape_id);
+    if (s->d_tabs) cudaFree(s->d_tabs);
+    for (void *q : s->tab_allocs) cudaFree(q);
     delete s;
     return SWARM_OK;
 }
@@ -252,14 +284,25 @@ int swarm_set_grid(swarm_sim *s, int32_t env0, int32_t count, const double *grid
         CU_TRY(cudaMemcpyAsync(s->d_stage, grid, need * sizeof(double), cudaMemcpyHostToDevice, st));
         src = s->d_stage;
     }
+    PoseArgs A;
+    A.n_shapes = s->fast_ok ? s->n_shapes : 0; A.n_g_cap = ngm;
+    A.tabs = s->d_tabs; A.shape_grid = s->d_shape_grid; A.shape_n_g = s->d_shape_ng;
+    A.pose = s->d_pose + env0; A.shape_id = s->d_shape_id + env0;
     k_pack_grid<<<count, 128, 0, st>>>(src, (long)2 * ngm, s->buf.n_g + env0, s->K.n_g_pad,
                                        reinterpret_cast<double2 *>(s->buf.grid) + (size_t)env0 * s->K.n_g_pad,
                                        reinterpret_cast<float4 *>(s->buf.word_box) + (size_t)env0 * s->K.n_words,
-                                       s->buf.frame + (size_t)env0 * 2);
+                                       s->buf.frame + (size_t)env0 * 2, A);
     CU_TRY(cudaGetLastError());
     s->launches++;
+    // which of these envs matched a library shape (lookup scan) — the host mirror decides which kernel a step launches
+    std::vector<int> ids(count);
+    CU_TRY(cudaMemcpyAsync(ids.data(), s->d_shape_id + env0, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
     // thr/n_g host vectors must outlive the async copies
     CU_TRY(cudaStreamSynchronize(st));
+    for (int k = 0; k < count; ++k) {
+        s->n_unposed += (ids[k] < 0) - (s->h_shape_id[env0 + k] < 0);
+        s->h_shape_id[env0 + k] = ids[k];
+    }
     s->prior_dirty = true;
     return SWARM_OK;
 }
@@ -283,8 +326,94 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     CU_TRY(cudaMemcpy(s->d_shape_thr, thr.data(), sizeof(double) * n_shapes, cudaMemcpyHostToDevice));
     s->n_shapes = n_shapes;
     s->shape_l_cell.assign(l_cell, l_cell + n_shapes);
+
+    // ---- lookup-scan tables (see ShapeTab / k_build_bins).  Any earlier pose refers to the old library: forget it.
+    for (void *q : s->tab_allocs) cudaFree(q);
+    s->tab_allocs.clear();
+    if (s->d_tabs) { cudaFree(s->d_tabs); s->d_tabs = nullptr; }
+    CU_TRY(cudaMemset(s->d_shape_id, 0xFF, sizeof(int) * (size_t)s->cfg.num_envs));
+    std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), -1);
+    s->n_unposed = s->cfg.num_envs;
+    s->fast_ok = false;
+    s->h_tabs.assign(n_shapes, ShapeTab{});
+    // the lookup kernel serves single-warp envs with <= 1024 cells; rows per agent <= 32 and cells per row record <= 31
+    double l_min = l_cell[0];
+    for (int k = 1; k < n_shapes; ++k) l_min = std::min(l_min, l_cell[k]);
+    const double rr = s->cfg.d_sen / l_min;
+    const bool eligible = s->nt == 32 && s->K.n_words <= 32 && ngm <= 1023 && rr <= 14.9 && !s->cfg.brute_force_scan &&
+                          !getenv("SWARM_NO_LOOKUP_SCAN");
+    if (!eligible) return SWARM_OK;
+    const double half_extent = std::max(s->K.half_w, s->K.half_h);
+    // origin-frame positions the table must cover: |p| up to the walls (+ slack: they are soft), |offset| up to half - 1 (ENV:184-185)
+    const double Q = 1.4142135623730951 * ((half_extent + 0.25) + std::max(half_extent - 1.0, 0.0)) + 0.1;
+    int n_tables = 0;
+    for (int k = 0; k < n_shapes; ++k) {
+        const double *gx = grids + (size_t)k * 2 * ngm, *gy = gx + n_g[k];
+        const int n = n_g[k];
+        const double L = l_cell[k];
+        ShapeTab &T = s->h_tabs[k];
+        double ox_min = gx[0], oy_min = gy[0];
+        for (int c = 0; c < n; ++c) { ox_min = std::min(ox_min, gx[c]); oy_min = std::min(oy_min, gy[c]); }
+        // lattice recovery: every cell at (ox_min + ix L, oy_min + iy L), numbered row by row
+        bool ok = L > 0 && n >= 2;
+        std::vector<unsigned long long> rowmask;
+        std::vector<unsigned short> rowstart;
+        int ncols = 0, far_cell = 0; long prev_key = -1; double far_d2 = -1.0;
+        for (int c = 0; c < n && ok; ++c) {
+            const long ix = std::lround((gx[c] - ox_min) / L), iy = std::lround((gy[c] - oy_min) / L);
+            ok = ix >= 0 && ix < 64 && iy >= 0 && iy < 4096 && std::fabs(gx[c] - (ox_min + ix * L)) <= 1e-9 &&
+                 std::fabs(gy[c] - (oy_min + iy * L)) <= 1e-9 && iy * 64 + ix > prev_key;
+            if (!ok) break;
+            prev_key = iy * 64 + ix;
+            if ((long)rowmask.size() <= iy) { rowmask.resize(iy + 1, 0ull); rowstart.resize(iy + 1, (unsigned short)c); }
+            if (rowmask[iy] == 0ull) rowstart[iy] = (unsigned short)c;
+            rowmask[iy] |= 1ull << ix;
+            ncols = std::max(ncols, (int)ix + 1);
+            const double d2 = (gx[c] - gx[0]) * (gx[c] - gx[0]) + (gy[c] - gy[0]) * (gy[c] - gy[0]);
+            if (d2 > far_d2) { far_d2 = d2; far_cell = c; }
+        }
+        if (!ok || far_cell == 0) continue;                          // not a lattice shape: its envs use the general scan
+        for (size_t r = 0; r < rowmask.size(); ++r) if (rowmask[r] == 0ull) rowstart[r] = (r ? rowstart[r - 1] : 0);
+        const double h = 0.5 * L;
+        const int nb = (int)std::ceil(2.0 * Q / h);
+        if ((size_t)nb * nb > (size_t)4 << 20) continue;             // table would be unreasonably large
+        unsigned long long *d_rowmask = nullptr; unsigned short *d_rowstart = nullptr, *d_spill = nullptr; uint2 *d_bins = nullptr;
+        unsigned *d_cursor = nullptr;
+        const unsigned spill_cap = (unsigned)nb * nb * 2u;
+        CU_TRY(cudaMalloc(&d_rowmask, sizeof(unsigned long long) * rowmask.size())); s->tab_allocs.push_back(d_rowmask);
+        CU_TRY(cudaMalloc(&d_rowstart, sizeof(unsigned short) * rowstart.size())); s->tab_allocs.push_back(d_rowstart);
+        CU_TRY(cudaMalloc(&d_bins, sizeof(uint2) * (size_t)nb * nb)); s->tab_allocs.push_back(d_bins);
+        CU_TRY(cudaMalloc(&d_spill, sizeof(unsigned short) * (size_t)spill_cap)); s->tab_allocs.push_back(d_spill);
+        CU_TRY(cudaMalloc(&d_cursor, sizeof(unsigned))); s->tab_allocs.push_back(d_cursor);
+        CU_TRY(cudaMemcpy(d_rowmask, rowmask.data(), sizeof(unsigned long long) * rowmask.size(), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_rowstart, rowstart.data(), sizeof(unsigned short) * rowstart.size(), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemset(d_cursor, 0, sizeof(unsigned)));
+        k_build_bins<<<(nb * nb + 127) / 128, 128>>>(s->d_shape_grid + (size_t)k * 2 * ngm, n, -Q, h, nb, d_bins, d_spill, d_cursor, spill_cap);
+        CU_TRY(cudaGetLastError());
+        s->launches++;
+        T.ox_min = ox_min; T.oy_min = oy_min; T.inv_l = 1.0 / L; T.q0 = -Q; T.inv_h = 1.0 / h;
+        T.ncols = ncols; T.nrows = (int)rowmask.size(); T.nb = nb; T.far_cell = far_cell;
+        T.rowmask = d_rowmask; T.rowstart = d_rowstart; T.bins = d_bins; T.spill = d_spill;
+        ++n_tables;
+    }
+    CU_TRY(cudaDeviceSynchronize());
+    if (n_tables == 0) return SWARM_OK;
+    CU_TRY(cudaMalloc(&s->d_tabs, sizeof(ShapeTab) * n_shapes));
+    CU_TRY(cudaMemcpy(s->d_tabs, s->h_tabs.data(), sizeof(ShapeTab) * n_shapes, cudaMemcpyHostToDevice));
+    s->K.shapes = s->d_tabs;
+    const int rows_per_agent = (2.0 * (rr + 2e-3) + 2.0 <= 16.0) ? 16 : 32;
+    s->rec_cap = s->nt * rows_per_agent;
+    s->K.rec_cap = s->rec_cap;
+    s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, s->cfg.emit_indices != 0, s->cfg.num_obs_grid_max, 2, s->rec_cap);
+    for (int f32 = 0; f32 < 2; ++f32)
+        for (int emit = 0; emit < 2; ++emit)
+            CU_TRY(cudaFuncSetAttribute((const void *)pick_fast(f32 != 0, emit != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+    s->fast_ok = true;
     return SWARM_OK;
 }
+
+/* 1 if the next swarm_step / swarm_observe runs the lookup-scan kernel (every env's grid matched a library shape), else 0 */
+int swarm_fast_path(const swarm_sim *s) { return (s && s->fast_ok && s->split && s->n_unposed == 0) ? 1 : 0; }
 
 int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
                 double *info_dev, void *stream) {
@@ -299,10 +428,17 @@ int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offs
     R.in_thresh = s->buf.in_thresh; R.wbox = reinterpret_cast<float4 *>(s->buf.word_box); R.frame = s->buf.frame;
     R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = env_mask; R.env_list = nullptr;
     R.seed = seed; R.episode = episode; R.env_offset = env_offset;
+    R.pose = s->fast_ok ? s->d_pose : nullptr; R.shape_id = s->fast_ok ? s->d_shape_id : nullptr; R.tabs = s->d_tabs;
     k_reset<<<s->cfg.num_envs, 128, 0, (cudaStream_t)stream>>>(R);
     CU_TRY(cudaGetLastError());
     s->launches++;
     s->prior_dirty = true;
+    if (s->fast_ok && !env_mask) {
+        // every env now has a library pose (a shape without a table leaves its envs unmatched: rebuild the count)
+        bool all = true;
+        for (int k = 0; k < s->n_shapes; ++k) all = all && s->h_tabs[k].nb != 0;
+        if (all) { std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), 0); s->n_unposed = 0; }
+    }
     return swarm_observe(s, stream);     // ENV:221; a masked reset re-observes every env (idempotent for the untouched ones)
 }
 
@@ -323,6 +459,9 @@ int swarm_reset_envs(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env
     R.in_thresh = s->buf.in_thresh; R.wbox = reinterpret_cast<float4 *>(s->buf.word_box); R.frame = s->buf.frame;
     R.nearest = s->buf.nearest_cell; R.info = info_dev; R.mask = nullptr; R.env_list = env_list_dev;
     R.seed = seed; R.episode = episode; R.env_offset = env_offset;
+    // (a partial reset keeps the host's matched-env count: matched envs stay matched; unmatched ones in the list become
+    // matched on the device but the host cannot tell which, so the general kernel stays in use until a full reset / set_grid)
+    R.pose = s->fast_ok ? s->d_pose : nullptr; R.shape_id = s->fast_ok ? s->d_shape_id : nullptr; R.tabs = s->d_tabs;
     k_reset<<<count, 128, 0, (cudaStream_t)stream>>>(R);
     CU_TRY(cudaGetLastError());
     s->launches++;
@@ -423,7 +562,8 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
     if (s->split) {
         pick_step(f32, dyn, emit, s->nt, 1)<<<ctas, s->nt, s->smem, st>>>(K);
-        pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
+        if (swarm_fast_path(s)) pick_fast(f32, emit)<<<ctas, s->nt, s->smem_fast, st>>>(K);
+        else pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
         s->launches += 2;
     } else {
         pick_step(f32, dyn, emit, s->nt, 0)<<<ctas, s->nt, s->smem, st>>>(K);
@@ -607,7 +747,7 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid, d_box, d_frame);
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid, d_box, d_frame, PoseArgs{});
     LEG_TRY(W, cudaMemset(d_near, 0, (size_t)n_a * 4));
     K.wbox = d_box; K.frame = d_frame;
     K.p = d_p; K.dp = d_dp; K.grid = d_grid; K.n_g = d_ng; K.in_thresh = d_thr;
@@ -709,7 +849,7 @@ void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_c
     LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
     LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid, d_box, d_frame);
+    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid, d_box, d_frame, PoseArgs{});
     k_prior<double><<<1, n_a < 256 ? round32(n_a) : 256>>>(n_a, topo_nei_max, d_p, d_dp, d_grid, n_g_pad, d_ng, d_thr, d_nbr, r_avoid, d_out);
     LEG_TRY(W, cudaGetLastError());
     LEG_TRY(W, cudaMemcpy(a_prior, d_out, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));

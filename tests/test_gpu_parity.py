@@ -14,9 +14,34 @@ from tests.helpers import GOLDEN_CASES, goal_seeking_action, load_golden, load_s
 pytestmark = pytest.mark.gpu
 
 
+SCAN = {"mode": "lookup"}
+
+
+@pytest.fixture(params=["lookup", "culled"], autouse=True)
+def scan_mode(request):
+    """Every test of this module runs twice: with the shape library installed (grids set through set_grid are recognised as
+    rigid transforms of library shapes -> the lookup-scan kernel, where eligible) and without it (general culled scan)."""
+    SCAN["mode"] = request.param
+    yield request.param
+    SCAN["mode"] = "lookup"
+
+
 def make_sim(E, n_a, n_g_max, r_avoid, **kw):
     from marl_llm_b200.batched import BatchedAssemblySim
-    return BatchedAssemblySim(E, n_a, n_g_max, r_avoid, **kw)
+    shapes = load_shapes()
+    lookup = SCAN["mode"] == "lookup"
+    if lookup:
+        n_g_max = max(n_g_max, int(shapes["n_g"].max()))
+    sim = BatchedAssemblySim(E, n_a, n_g_max, r_avoid, **kw)
+    if lookup:
+        sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+    sim.expect_fast = lookup and n_a <= 32 and not kw.get("brute_force_scan", False)
+    return sim
+
+
+def check_scan_mode(sim):
+    """After the grids are in: the kernel that will run is the one this test variant is about."""
+    assert sim.fast_path == sim.expect_fast, (sim.fast_path, SCAN["mode"])
 
 
 def sim_snapshot(sim, e=None):
@@ -35,8 +60,9 @@ def test_golden_trajectories_bit_exact(case):
                    is_periodic=bool(g.get("is_periodic", 0)))
 
     def reset_fn(g):
-        blocks, ng = sim.pack_grids([g["grid_center"]], n_g)
+        blocks, ng = sim.pack_grids([g["grid_center"]], sim.n_g_max)
         sim.set_grid(blocks, ng, [float(g["l_cell"])])
+        check_scan_mode(sim)
         sim.set_state(g["p0"][None], g["dp0"][None])
         sim.observe()
         return sim_snapshot(sim, 0)
@@ -67,6 +93,7 @@ def load_batch(sim, ob, params, grids, P, DP):
     ob.p[:], ob.dp[:] = P, DP
     blocks, n_g = sim.pack_grids(grids, sim.n_g_max)
     sim.set_grid(blocks, n_g, [p_.l_cell for p_ in params])
+    check_scan_mode(sim)
     sim.set_state(P, DP)
 
 
@@ -560,6 +587,7 @@ def test_config3_full_size_65536_envs_properties():
     sims = [make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32) for _ in range(2)]
     for s_ in sims:
         s_.set_grid(blocks, n_g, l_cell); s_.set_state(p, dp); s_.observe()
+        check_scan_mode(s_)
     pick = np.random.RandomState(0).choice(E, 128, replace=False)
     params = [orc.make_params(n_a, int(n_g[e]), float(l_cell[e]), r_avoid) for e in pick]
     ob = orc.OracleBatch(params, nthreads=16)
