@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--regime", default="both", choices=["both", "random", "converged"],
                     help="headline = the first regime run (random: U(-1,1) actions, staggered 200-step episodes with auto-reset)")
     ap.add_argument("--episode-length", type=int, default=200, help="CFG:181")
+    ap.add_argument("--reset-cohorts", type=int, default=25, help="envs are auto-reset in this many staggered cohorts (<= episode length)")
     ap.add_argument("--brute-force-scan", action="store_true", help="A/B: disable the word-box culling of the grid scan")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -325,14 +326,20 @@ def main():
     for r in range(ring):
         sim.fill_actions(acts[r], seed=226, step=r, env_offset=env0)
     EP = args.episode_length
-    lists = [torch.arange(ph, E, EP, dtype=torch.int32, device="cuda") for ph in range(EP)]
+    # auto-reset cohorts: env e belongs to cohort e mod C and is reset when t = (EP / C) * cohort (mod EP): every episode lasts
+    # exactly EP steps, the batch holds C evenly spaced episode ages at any time
+    C_ = max(1, min(args.reset_cohorts, EP))
+    stride = EP // C_
+    lists = [torch.arange(ph // stride, E, C_, dtype=torch.int32, device="cuda") if (ph % stride == 0 and ph // stride < C_)
+             else torch.empty(0, dtype=torch.int32, device="cuda") for ph in range(EP)]
     clock = {"t": 0}
     peak, peak_src = measured_hbm_peak()
 
     def step_random():
         """One step of the 'random' regime: U(-1,1) actions (BASELINE config 1/3) for every env, then the auto-reset of the
-        envs whose 200-step episode (CFG:181) just ended.  Env e resets when t = e (mod 200), so the batch is a stationary
-        mixture of episode ages and the measured rate does not depend on where the timed window starts or how long it is."""
+        envs whose 200-step episode (CFG:181) just ended.  The envs form 25 cohorts whose episodes start 8 steps apart, so the
+        batch is a stationary mixture of episode ages and the measured rate does not depend on where the timed window starts
+        or how long it is (a cohort's reset + first observation are two small extra launches inside the timed region)."""
         t = clock["t"]
         sim.step(acts[t % ring])
         due = lists[t % EP]
@@ -483,9 +490,9 @@ def main():
             "config": {"workload": (f"assembly env, {n_a} agents x {E} envs per GPU, env-sharded (BASELINE config 3)" if n_a == 30 else
                                     f"large swarm: {n_a} agents x {E} envs per GPU (BASELINE config 4)"),
                        "n_a": n_a, "envs_per_gpu": E, "layout": args.layout, "regime": want[0],
-                       "episodes": f"{EP}-step episodes, env e auto-resets (swarm_reset_envs) when t = e mod {EP}; the reset launches are inside the timed region, reset envs are not counted as extra agent-steps",
+                       "episodes": f"{EP}-step episodes, auto-reset (swarm_reset_envs) in {C_} cohorts whose episodes start {stride} steps apart; the reset launches are inside the timed region, reset envs are not counted as extra agent-steps",
                        "out_dtype": "f64" if parity else "f32", "state_dtype": "f64",
-                       "grid_scan": "all-pairs" if args.brute_force_scan else "word-box culled",
+                       "grid_scan": "all-pairs" if args.brute_force_scan else ("lookup (per-shape bin table + lattice rows)" if sim.fast_path else "word-box culled"),
                        "l2": f"working set per step {bytes_per_launch / 1e6:.0f} MB >> 126 MB L2 (no flush needed)",
                        "actions": f"ring of {ring} pre-generated device buffers"},
             "regimes": regimes,

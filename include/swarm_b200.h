@@ -160,10 +160,12 @@ int swarm_set_grid(swarm_sim *sim, int32_t env0, int32_t count, const double *gr
  * count and cell size (ENV:116,163). */
 int swarm_set_shapes(swarm_sim *sim, int32_t n_shapes, const double *grids, const int32_t *n_g, const double *l_cell);
 
-/* 1 if the next step / observe runs the lookup-scan kernel: a shape library was set, the configuration is eligible (single-warp
+/* != 0 if the next step / observe runs the lookup-scan kernel: a shape library was set, the configuration is eligible (single-warp
  * envs, <= 1023 cells, d_sen / l_cell <= 14.9, lattice shapes) and EVERY env's current grid was recognised as a rigid transform
  * of a library shape (swarm_set_grid checks each grid against the library to 1e-9; swarm_reset knows the pose).  Otherwise the
- * general culled scan runs; results are identical either way. */
+ * general culled scan runs; results are identical either way.  2 = in addition every pose is known exactly (the device built
+ * the grids itself: swarm_reset), so the kernel recomputes the cells it needs from the library instead of reading each env's
+ * stored copy. */
 int swarm_fast_path(const swarm_sim *sim);
 
 /* reset() on the device, ENV:156-223: shape pick, rotation, offset, initial positions and velocities for every env (or

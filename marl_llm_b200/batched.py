@@ -248,8 +248,9 @@ class BatchedAssemblySim:
 
     @property
     def fast_path(self):
-        """True if the next step runs the lookup-scan kernel (shape library set, every env's grid recognised)."""
-        return bool(self.lib.swarm_fast_path(self._h))
+        """0: the general culled scan runs next; 1: the lookup-scan kernel (shape library set, every env's grid recognised);
+        2: lookup scan with exactly known poses (grids built by reset()): cells recomputed from the library."""
+        return int(self.lib.swarm_fast_path(self._h))
 
     @property
     def observed(self):

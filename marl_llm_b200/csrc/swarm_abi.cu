@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -66,6 +67,19 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, i
 
 typedef void (*step_fn_t)(const KParams);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per kernel function and process-wide: several handles (and the legacy entry
+// points) share the instantiations, so the attribute is only ever RAISED (a handle with a smaller need must not shrink it)
+cudaError_t raise_smem_limit(const void *fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void *, size_t> high;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &h = high[fn];
+    if (bytes <= h) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) h = bytes;
+    return e;
+}
+
 // phase 0 = the whole step in one launch; 1 / 2 = its two halves (single-warp envs)
 template <typename OUT, int MAXT, int PH>
 step_fn_t pick2(bool dyn, bool emit) {
@@ -73,9 +87,14 @@ step_fn_t pick2(bool dyn, bool emit) {
     return emit ? (step_fn_t)k_step<OUT, false, true, MAXT, PH> : (step_fn_t)k_step<OUT, false, false, MAXT, PH>;
 }
 // second half with the lookup scan (single-warp envs whose grids all have a known pose)
-step_fn_t pick_fast(bool f32, bool emit) {
-    if (f32) return emit ? (step_fn_t)k_step<float, false, true, 128, 2, true> : (step_fn_t)k_step<float, false, false, 128, 2, true>;
-    return emit ? (step_fn_t)k_step<double, false, true, 128, 2, true> : (step_fn_t)k_step<double, false, false, 128, 2, true>;
+// (exact: every pose is known exactly -> cells recomputed from the shape library instead of read per env)
+step_fn_t pick_fast(bool f32, bool emit, bool exact) {
+    if (exact) {
+        if (f32) return emit ? (step_fn_t)k_step<float, false, true, 128, 2, 2> : (step_fn_t)k_step<float, false, false, 128, 2, 2>;
+        return emit ? (step_fn_t)k_step<double, false, true, 128, 2, 2> : (step_fn_t)k_step<double, false, false, 128, 2, 2>;
+    }
+    if (f32) return emit ? (step_fn_t)k_step<float, false, true, 128, 2, 1> : (step_fn_t)k_step<float, false, false, 128, 2, 1>;
+    return emit ? (step_fn_t)k_step<double, false, true, 128, 2, 1> : (step_fn_t)k_step<double, false, false, 128, 2, 1>;
 }
 step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt, int phase = 0) {
     if (nt <= 128) {
@@ -142,7 +161,7 @@ struct swarm_sim {
     // lookup scan: per-shape tables, per-env pose (library-owned device memory), host mirror of which envs are matched
     ShapeTab *d_tabs; std::vector<void *> tab_allocs; std::vector<ShapeTab> h_tabs;
     double4 *d_pose; int *d_shape_id;
-    std::vector<int> h_shape_id; long n_unposed;
+    std::vector<int> h_shape_id; long n_unposed, n_inexact;   // envs without a pose / with a pose that is only 1e-9 accurate
     bool fast_ok;           // the shapes / sizes allow the lookup kernel at all
     int rec_cap; size_t smem_fast;
 };
@@ -217,14 +236,14 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
         for (int ph = 0; ph < 3; ++ph) {
             if (ph > 0 && s->nt > 128) continue;
             step_fn_t f = pick_step(cfg->out_dtype == SWARM_F32, dyn != 0, cfg->emit_indices != 0, s->nt, ph);
-            cudaError_t e = cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ph == 2 ? s->smem2 : s->smem));
+            cudaError_t e = raise_smem_limit((const void *)f, ph == 2 ? s->smem2 : s->smem);
             if (e != cudaSuccess) { delete s; return fail(SWARM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
         }
     s->pending = 0; s->last = 0; s->prior_dirty = true; s->observed = false; s->launches = 0;
     s->d_stage = nullptr; s->stage_cap = 0; s->d_act = nullptr; s->act_cap = 0;
     s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
     s->d_tabs = nullptr; s->d_pose = nullptr; s->d_shape_id = nullptr;
-    s->h_shape_id.assign(cfg->num_envs, -1); s->n_unposed = cfg->num_envs;
+    s->h_shape_id.assign(cfg->num_envs, -1); s->n_unposed = cfg->num_envs; s->n_inexact = cfg->num_envs;
     s->fast_ok = false; s->rec_cap = 0; s->smem_fast = 0;
     {
         cudaError_t e1 = cudaMalloc(&s->d_pose, sizeof(double4) * (size_t)cfg->num_envs);
@@ -300,7 +319,9 @@ int swarm_set_grid(swarm_sim *s, int32_t env0, int32_t count, const double *grid
     // thr/n_g host vectors must outlive the async copies
     CU_TRY(cudaStreamSynchronize(st));
     for (int k = 0; k < count; ++k) {
-        s->n_unposed += (ids[k] < 0) - (s->h_shape_id[env0 + k] < 0);
+        const int old = s->h_shape_id[env0 + k];
+        s->n_unposed += (ids[k] < 0) - (old < 0);
+        s->n_inexact += (ids[k] < 0 || !(ids[k] & POSE_EXACT)) - (old < 0 || !(old & POSE_EXACT));
         s->h_shape_id[env0 + k] = ids[k];
     }
     s->prior_dirty = true;
@@ -333,7 +354,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     if (s->d_tabs) { cudaFree(s->d_tabs); s->d_tabs = nullptr; }
     CU_TRY(cudaMemset(s->d_shape_id, 0xFF, sizeof(int) * (size_t)s->cfg.num_envs));
     std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), -1);
-    s->n_unposed = s->cfg.num_envs;
+    s->n_unposed = s->cfg.num_envs; s->n_inexact = s->cfg.num_envs;
     s->fast_ok = false;
     s->h_tabs.assign(n_shapes, ShapeTab{});
     // the lookup kernel serves single-warp envs with <= 1024 cells; rows per agent <= 32 and cells per row record <= 31
@@ -378,6 +399,11 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         const int nb = (int)std::ceil(2.0 * Q / h);
         if ((size_t)nb * nb > (size_t)4 << 20) continue;             // table would be unreasonably large
         unsigned long long *d_rowmask = nullptr; unsigned short *d_rowstart = nullptr, *d_spill = nullptr; uint2 *d_bins = nullptr;
+        double2 *d_cells = nullptr;
+        std::vector<double2> cells(n);
+        for (int c = 0; c < n; ++c) cells[c] = make_double2(gx[c], gy[c]);
+        CU_TRY(cudaMalloc(&d_cells, sizeof(double2) * n)); s->tab_allocs.push_back(d_cells);
+        CU_TRY(cudaMemcpy(d_cells, cells.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
         unsigned *d_cursor = nullptr;
         const unsigned spill_cap = (unsigned)nb * nb * 2u;
         CU_TRY(cudaMalloc(&d_rowmask, sizeof(unsigned long long) * rowmask.size())); s->tab_allocs.push_back(d_rowmask);
@@ -393,7 +419,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         s->launches++;
         T.ox_min = ox_min; T.oy_min = oy_min; T.inv_l = 1.0 / L; T.q0 = -Q; T.inv_h = 1.0 / h;
         T.ncols = ncols; T.nrows = (int)rowmask.size(); T.nb = nb; T.far_cell = far_cell;
-        T.rowmask = d_rowmask; T.rowstart = d_rowstart; T.bins = d_bins; T.spill = d_spill;
+        T.rowmask = d_rowmask; T.rowstart = d_rowstart; T.bins = d_bins; T.spill = d_spill; T.cells = d_cells;
         ++n_tables;
     }
     CU_TRY(cudaDeviceSynchronize());
@@ -407,13 +433,18 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, s->cfg.emit_indices != 0, s->cfg.num_obs_grid_max, 2, s->rec_cap);
     for (int f32 = 0; f32 < 2; ++f32)
         for (int emit = 0; emit < 2; ++emit)
-            CU_TRY(cudaFuncSetAttribute((const void *)pick_fast(f32 != 0, emit != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_fast));
+            for (int exact = 0; exact < 2; ++exact)
+                CU_TRY(raise_smem_limit((const void *)pick_fast(f32 != 0, emit != 0, exact != 0), s->smem_fast));
     s->fast_ok = true;
     return SWARM_OK;
 }
 
-/* 1 if the next swarm_step / swarm_observe runs the lookup-scan kernel (every env's grid matched a library shape), else 0 */
-int swarm_fast_path(const swarm_sim *s) { return (s && s->fast_ok && s->split && s->n_unposed == 0) ? 1 : 0; }
+/* which second-half kernel the next swarm_step / swarm_observe runs: 0 = general culled scan, 1 = lookup scan on the stored
+ * cells (every env's grid matched a library shape), 2 = lookup scan with cells recomputed from the library (every pose exact) */
+int swarm_fast_path(const swarm_sim *s) {
+    if (!(s && s->fast_ok && s->split && s->n_unposed == 0)) return 0;
+    return (s->n_inexact == 0 && !getenv("SWARM_NO_EXACT_POSE")) ? 2 : 1;
+}
 
 int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
                 double *info_dev, void *stream) {
@@ -437,7 +468,7 @@ int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offs
         // every env now has a library pose (a shape without a table leaves its envs unmatched: rebuild the count)
         bool all = true;
         for (int k = 0; k < s->n_shapes; ++k) all = all && s->h_tabs[k].nb != 0;
-        if (all) { std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), 0); s->n_unposed = 0; }
+        if (all) { std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), POSE_EXACT); s->n_unposed = 0; s->n_inexact = 0; }
     }
     return swarm_observe(s, stream);     // ENV:221; a masked reset re-observes every env (idempotent for the untouched ones)
 }
@@ -562,7 +593,7 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
     if (s->split) {
         pick_step(f32, dyn, emit, s->nt, 1)<<<ctas, s->nt, s->smem, st>>>(K);
-        if (swarm_fast_path(s)) pick_fast(f32, emit)<<<ctas, s->nt, s->smem_fast, st>>>(K);
+        if (const int fp = swarm_fast_path(s)) pick_fast(f32, emit, fp == 2)<<<ctas, s->nt, s->smem_fast, st>>>(K);
         else pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
         s->launches += 2;
     } else {
@@ -754,7 +785,7 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     K.obs = d_obs; K.reward = d_rew; K.prior_next = d_prior;
     K.nbr = d_nbr; K.in_flags = d_inf; K.nearest = d_near; K.sensed = d_sidx; K.occupied = d_occ;
     step_fn_t f = pick_step(false, false, true, nt);
-    LEG_TRY(W, cudaFuncSetAttribute((const void *)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LEG_TRY(W, raise_smem_limit((const void *)f, smem));
     f<<<1, nt, smem>>>(K);
     LEG_TRY(W, cudaGetLastError());
     LEG_TRY(W, cudaMemcpy(obs, d_obs, n_obs * 8, cudaMemcpyDeviceToHost));
