@@ -40,7 +40,7 @@ def load_shapes():
                 grid_origin=[np.ascontiguousarray(z["grid_coords"][k, :n_g[k]].T) for k in range(len(n_g))])
 
 
-def synth_batch(E, n_a, shapes, seed, regime):
+def synth_batch(E, n_a, shapes, seed, regime, with_pose=False):
     """Vectorised domain randomisation in the spirit of assembly.py:156-223 (shape, rotation, offset, initial p/dp).
     regime 'random': the reference's reset distribution.  'converged': agents start on cells of their shape so the
     in-shape / occupancy / subsample / reward branches are the common case."""
@@ -77,6 +77,8 @@ def synth_batch(E, n_a, shapes, seed, regime):
         dp = rng.uniform(-0.5, 0.5, (E, 2, n_a))
     else:
         dp = rng.uniform(-0.05, 0.05, (E, 2, n_a))
+    if with_pose:      # (shape, cos, sin, off_x, off_y) per env: the grids above are exactly grid_from_pose of these
+        return blocks, n_g, l_cell, p, dp, (k.astype(np.int32), c, s, off[:, 0].copy(), off[:, 1].copy())
     return blocks, n_g, l_cell, p, dp
 
 
@@ -396,8 +398,8 @@ def main():
                 step_random()
             ms, launches = timed(step_random, K, W)
         else:
-            blocks, n_g, l_cell, p, dp = synth_batch(E, n_a, shapes, 226 + rank, "converged")
-            sim.set_grid(blocks, n_g, l_cell)
+            blocks, n_g, l_cell, p, dp, pose = synth_batch(E, n_a, shapes, 226 + rank, "converged", with_pose=True)
+            sim.set_grid_pose(*pose)                                     # the device applies grid = R.origin + off itself
             sim.set_state(p, dp)
             sim.observe()
             sim.step(acts[0])                                            # produces the first prior action

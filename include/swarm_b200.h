@@ -160,6 +160,12 @@ int swarm_set_grid(swarm_sim *sim, int32_t env0, int32_t count, const double *gr
  * count and cell size (ENV:116,163). */
 int swarm_set_shapes(swarm_sim *sim, int32_t n_shapes, const double *grids, const int32_t *n_g, const double *l_cell);
 
+/* Target shapes for envs [env0, env0+count) as (library shape, pose) pairs chosen by the host: the device computes
+ * grid_center = R * origin + off itself, R = [[cos, sin], [-sin, cos]], every product and sum rounded separately (ENV:175-187
+ * evaluated without FMA).  shape_ids: HOST [count]; pose: HOST [count][4] = (cos, sin, off_x, off_y).  Same effect as
+ * swarm_set_grid with that grid, and the pose is known exactly (swarm_fast_path may then return 2). */
+int swarm_set_grid_pose(swarm_sim *sim, int32_t env0, int32_t count, const int32_t *shape_ids, const double *pose, void *stream);
+
 /* != 0 if the next step / observe runs the lookup-scan kernel: a shape library was set, the configuration is eligible (single-warp
  * envs, <= 1023 cells, d_sen / l_cell <= 14.9, lattice shapes) and EVERY env's current grid was recognised as a rigid transform
  * of a library shape (swarm_set_grid checks each grid against the library to 1e-9; swarm_reset knows the pose).  Otherwise the

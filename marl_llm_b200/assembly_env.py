@@ -120,6 +120,14 @@ class AssemblySwarmEnv:
 
     def _push_grid(self):
         E = self.num_envs
+        poses = getattr(self, "_poses", None)
+        if poses is not None and self._sim.shapes_installed:
+            # reset() chose (shape, angle, offset) itself and NumPy's grid equals the device's own R.origin + off bit for bit
+            # (checked in _reset_one): hand over the pose, the device rebuilds the identical grid and knows the pose exactly
+            k, c, s, ox, oy = (np.array(v) for v in zip(*poses))
+            self._sim.set_grid_pose(k, c, s, ox, oy)
+            self._grid_dirty = False
+            return
         grids = [self._grid_center] if E == 1 else list(self._grid_center)
         n_g = max(g.shape[1] for g in grids)
         if n_g > self._n_g_cap:                                          # eval may install a bigger shape
@@ -168,6 +176,7 @@ class AssemblySwarmEnv:
     def grid_center(self, v):
         self._grid_center = np.ascontiguousarray(v, dtype=np.float64) if self.num_envs == 1 else v
         self._grid_dirty = True
+        self._poses = None             # a caller-provided grid: the simulator recognises its pose itself (or uses the general scan)
 
     @property
     def l_cell(self):
@@ -177,6 +186,7 @@ class AssemblySwarmEnv:
     def l_cell(self, v):
         self._l_cell = v
         self._grid_dirty = True
+        self._poses = None
 
     @property
     def n_g(self):
@@ -216,11 +226,19 @@ class AssemblySwarmEnv:
             p = np.random.uniform(-1, 1, (2, self.n_a)) + np.array(
                 [[np.random.uniform(-hw + 1, hw - 1), np.random.uniform(-hh + 1, hh - 1)]]).T
         dp = np.random.uniform(-0.5, 0.5, (self.dim, self.n_a))
+        # does NumPy's np.dot(R, origin) + off equal the separately rounded R.origin + off the device computes?  (it does unless
+        # the BLAS behind np.dot contracts into FMAs); if so the pose can be handed over instead of the grid
+        o0 = np.asarray(self.grid_center_origins[k], dtype=np.float64).T
+        alt = BatchedAssemblySim.grid_from_pose(o0, R[0, 0], R[0, 1], off[0, 0], off[1, 0])
+        self._pose_one = (k, R[0, 0], R[0, 1], off[0, 0], off[1, 0]) if np.array_equal(alt, grid) else None
         return l_cell, origin, grid, sbp_origin, sbp, p, dp
 
     def reset(self):
         self.simulation_time = 0
-        outs = [self._reset_one() for _ in range(self.num_envs)]
+        outs, poses = [], []
+        for _ in range(self.num_envs):
+            outs.append(self._reset_one())
+            poses.append(self._pose_one)
         one = self.num_envs == 1
         self._l_cell = outs[0][0] if one else np.array([o[0] for o in outs])
         self.grid_center_origin = outs[0][1] if one else [o[1] for o in outs]
@@ -230,6 +248,7 @@ class AssemblySwarmEnv:
         self.boundary_pos = np.array([-self.boundary_width_half, self.boundary_height_half,
                                       self.boundary_width_half, -self.boundary_height_half], dtype=np.float64)
         self.d_sen = 0.4
+        self._poses = poses if all(q is not None for q in poses) else None
         self._push_grid()
         self._sim.set_state(np.stack([o[5] for o in outs]), np.stack([o[6] for o in outs]))
         self.ddp = np.zeros((2, self.n_a))

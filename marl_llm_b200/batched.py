@@ -117,6 +117,7 @@ class BatchedAssemblySim:
         self._h = h
         self.l_cell = np.zeros(E)
         self.n_g = np.zeros(E, dtype=np.int32)
+        self.shapes_installed = False
 
     # ------------------------------------------------------------------------------------------------
     def close(self):
@@ -155,6 +156,23 @@ class BatchedAssemblySim:
         self.n_g[env0:env0 + count] = n_g
         self.l_cell[env0:env0 + count] = l_cell
 
+    def set_grid_pose(self, shape_ids, cos, sin, off_x, off_y, env0=0):
+        """Target shapes as (library shape, pose): the device computes grid_center = R.origin + off itself (assembly.py:175-187,
+        R = [[cos, sin], [-sin, cos]], products and sums rounded separately).  Needs set_shapes().  Same effect as set_grid with
+        the grid `grid_from_pose` returns; the simulator then knows each pose exactly."""
+        ids = np.ascontiguousarray(shape_ids, dtype=np.int32).reshape(-1)
+        pose = np.ascontiguousarray(np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), ids.shape)
+                                              for v in (cos, sin, off_x, off_y)], axis=1))
+        check(self.lib.swarm_set_grid_pose(self._h, env0, ids.shape[0], C.c_void_p(ids.ctypes.data), C.c_void_p(pose.ctypes.data),
+                                           self._stream()), "swarm_set_grid_pose")
+        self.n_g[env0:env0 + ids.shape[0]] = self.shape_n_g[ids]
+        self.l_cell[env0:env0 + ids.shape[0]] = self.shape_l_cells[ids]
+
+    @staticmethod
+    def grid_from_pose(origin, cos, sin, off_x, off_y):
+        """The grid set_grid_pose installs for one env, computed on the host with the same roundings ([2, n_g] float64)."""
+        return np.stack([(cos * origin[0] + sin * origin[1]) + off_x, ((-sin) * origin[0] + cos * origin[1]) + off_y])
+
     @staticmethod
     def pack_grids(grids, n_g_max):
         """list of [2, n_g] arrays -> ([count, 2*n_g_max] block array, n_g[count])"""
@@ -174,6 +192,7 @@ class BatchedAssemblySim:
         check(self.lib.swarm_set_shapes(self._h, len(grid_origins), C.c_void_p(blocks.ctypes.data), C.c_void_p(n_g.ctypes.data),
                                         C.c_void_p(l_cells.ctypes.data)), "swarm_set_shapes")
         self.shape_l_cells, self.shape_n_g = l_cells.copy(), n_g.copy()
+        self.shapes_installed = True
 
     def reset(self, seed, episode=0, env_offset=0, env_mask=None):
         """reset() of assembly.py:156-223 for all envs (or those where env_mask is True) on the device, then the first

@@ -439,6 +439,47 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     return SWARM_OK;
 }
 
+/* Target shapes for envs [env0, env0 + count) given as (library shape, pose): grid_center = R * origin + off computed on the
+ * device with the reference's roundings (ENV:175-187).  shape_ids [count] and pose [count][4] = (cos, sin, off_x, off_y) are
+ * HOST arrays.  Equivalent to swarm_set_grid with that grid, but the pose is then known exactly (see swarm_fast_path). */
+int swarm_set_grid_pose(swarm_sim *s, int32_t env0, int32_t count, const int32_t *shape_ids, const double *pose, void *stream) {
+    if (!s || !shape_ids || !pose) return fail(SWARM_ERR_INVALID, "null argument");
+    if (env0 < 0 || count <= 0 || env0 + count > s->cfg.num_envs) return fail(SWARM_ERR_INVALID, "env range out of bounds");
+    if (s->n_shapes <= 0) return fail(SWARM_ERR_INVALID, "swarm_set_grid_pose before swarm_set_shapes");
+    for (int k = 0; k < count; ++k)
+        if (shape_ids[k] < 0 || shape_ids[k] >= s->n_shapes) return fail(SWARM_ERR_INVALID, "shape id out of range");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    const size_t need = (size_t)count * 5;                       // staging: ids (as doubles' worth of space) + poses
+    if (need > s->stage_cap) {
+        if (s->d_stage) CU_TRY(cudaFree(s->d_stage));
+        s->d_stage = nullptr; s->stage_cap = 0;
+        CU_TRY(cudaMalloc(&s->d_stage, need * sizeof(double)));
+        s->stage_cap = need;
+    }
+    double4 *d_pose_in = reinterpret_cast<double4 *>(s->d_stage);
+    int *d_ids = reinterpret_cast<int *>(s->d_stage + (size_t)count * 4);
+    CU_TRY(cudaMemcpyAsync(d_pose_in, pose, sizeof(double) * 4 * count, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_ids, shape_ids, sizeof(int) * count, cudaMemcpyHostToDevice, st));
+    k_grid_from_pose<<<count, 128, 0, st>>>(s->K.n_g_pad, s->cfg.n_g_max, s->d_shape_grid, s->d_shape_ng, s->d_shape_thr,
+                                            s->fast_ok ? s->d_tabs : nullptr, d_ids, d_pose_in,
+                                            reinterpret_cast<double2 *>(s->buf.grid) + (size_t)env0 * s->K.n_g_pad, s->buf.n_g + env0,
+                                            s->buf.in_thresh + env0, reinterpret_cast<float4 *>(s->buf.word_box) + (size_t)env0 * s->K.n_words,
+                                            s->buf.frame + (size_t)env0 * 2, s->d_pose + env0, s->d_shape_id + env0);
+    CU_TRY(cudaGetLastError());
+    s->launches++;
+    CU_TRY(cudaStreamSynchronize(st));                           // the host arrays may go away
+    for (int k = 0; k < count; ++k) {
+        const int old = s->h_shape_id[env0 + k];
+        const int now = (s->fast_ok && s->h_tabs[shape_ids[k]].nb) ? (shape_ids[k] | POSE_EXACT) : -1;
+        s->n_unposed += (now < 0) - (old < 0);
+        s->n_inexact += (now < 0) - (old < 0 || !(old & POSE_EXACT));
+        s->h_shape_id[env0 + k] = now;
+    }
+    s->prior_dirty = true;
+    return SWARM_OK;
+}
+
 /* which second-half kernel the next swarm_step / swarm_observe runs: 0 = general culled scan, 1 = lookup scan on the stored
  * cells (every env's grid matched a library shape), 2 = lookup scan with cells recomputed from the library (every pose exact) */
 int swarm_fast_path(const swarm_sim *s) {

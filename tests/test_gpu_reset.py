@@ -115,3 +115,50 @@ def test_shape_and_spawn_statistics():
     assert abs(info[:, 5].mean() - 0.5) < 0.05                     # U(-1, 1) > 0
     dp = sim.dp.cpu().numpy()
     assert abs(dp.mean()) < 0.01 and abs(dp.std() - 1 / np.sqrt(12)) < 0.01
+
+
+def test_set_grid_pose_builds_the_host_grid_bit_for_bit_and_rollout_matches_oracle():
+    """swarm_set_grid_pose: the device applies grid = R.origin + off itself (assembly.py:175-187).  The stored cells equal the
+    host's separately rounded evaluation bit for bit; the pose is then known exactly (fast_path == 2: cells recomputed from
+    the shape library) and a goal-seeking rollout follows the oracle on every output, as does the same batch fed through
+    set_grid (pose detected, fast_path == 1) and through the general scan (no shape library)."""
+    from marl_llm_b200.batched import BatchedAssemblySim
+    E, n_a = 64, 30
+    sim, shapes, r_avoid, ngm = make(E, n_a)
+    rng = np.random.RandomState(12)
+    k = rng.randint(0, 7, E)
+    ang = np.pi * rng.uniform(-1, 1, E)
+    cs, sn, off = np.cos(ang), np.sin(ang), rng.uniform(-1.4, 1.4, (E, 2))
+    grids = [BatchedAssemblySim.grid_from_pose(shapes["grid_origin"][k[e]], cs[e], sn[e], off[e, 0], off[e, 1]) for e in range(E)]
+    sim.set_grid_pose(k, cs, sn, off[:, 0], off[:, 1])
+    assert sim.fast_path == 2
+    dev_grid, n_g = sim._grid.cpu().numpy(), sim._n_g.cpu().numpy()
+    for e in range(E):
+        assert n_g[e] == grids[e].shape[1] and np.array_equal(dev_grid[e, :n_g[e]].T, grids[e]), e
+    detected = BatchedAssemblySim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    detected.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+    general = BatchedAssemblySim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    blocks, ng = sim.pack_grids(grids, ngm)
+    for other in (detected, general):
+        other.set_grid(blocks, ng, [float(shapes["l_cell"][k[e]]) for e in range(E)])
+    assert detected.fast_path == 1 and general.fast_path == 0
+    params = [orc.make_params(n_a, grids[e].shape[1], float(shapes["l_cell"][k[e]]), r_avoid) for e in range(E)]
+    ob = orc.OracleBatch(params, nthreads=8, ng_max=ngm)
+    for e in range(E):
+        ob.set_grid(e, grids[e])
+        c = rng.choice(grids[e].shape[1], n_a // 2, replace=False)      # half of each swarm starts on cells: in-shape from the start
+        ob.p[e] = rng.uniform(-2.4, 2.4, (2, n_a)); ob.p[e][:, :n_a // 2] = grids[e][:, c] + rng.normal(0, 0.01, (2, n_a // 2))
+    ob.dp[:] = rng.uniform(-0.5, 0.5, ob.dp.shape)
+    for s_ in (sim, detected, general):
+        s_.set_state(ob.p, ob.dp); s_.observe()
+    ob.observe(with_reward=True)
+    for t in range(60):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        ob.step(a)
+        for s_ in (sim, detected, general):
+            s_.step(torch.from_numpy(a).cuda())
+            for name, got, ref in (("p", s_.p, ob.p), ("obs", s_.obs, ob.obs), ("reward", s_.reward, ob.reward), ("a_prior", s_.a_prior, ob.a_prior),
+                                   ("nbr", s_.neighbor_index, ob.neighbor_index), ("in_flags", s_.in_flags, ob.in_flags),
+                                   ("sensed", s_.sensed_index, ob.sensed_index), ("occupied", s_.occupied_index, ob.occupied_index)):
+                assert np.array_equal(got.cpu().numpy(), ref), (name, t, s_.fast_path)
+    assert ob.in_flags.sum() > 500 and ob.reward.sum() > 0
