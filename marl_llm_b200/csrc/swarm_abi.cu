@@ -60,6 +60,7 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, i
         b += (size_t)TOPO * nt * sizeof(int);                                                       // neighbour list
         b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
     }
+    if (rec_cap >= 0) b += (size_t)64 * (8 + 8 + 8 + 2);                                            // lookup scan: lattice tables of the env's shape
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
     if (nt == 32 && n_words <= 32 && scratch > ring) b += scratch;   // aliases the TMA ring when it fits
     return b;
@@ -163,6 +164,7 @@ struct swarm_sim {
     double4 *d_pose; int *d_shape_id;
     std::vector<int> h_shape_id; long n_unposed, n_inexact;   // envs without a pose / with a pose that is only 1e-9 accurate
     bool fast_ok;           // the shapes / sizes allow the lookup kernel at all
+    bool xy_exact;          // every library shape has bit-identical x per lattice column and y per lattice row
     int rec_cap; size_t smem_fast;
 };
 
@@ -244,7 +246,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     s->d_shape_grid = nullptr; s->d_shape_ng = nullptr; s->d_shape_thr = nullptr; s->n_shapes = 0;
     s->d_tabs = nullptr; s->d_pose = nullptr; s->d_shape_id = nullptr;
     s->h_shape_id.assign(cfg->num_envs, -1); s->n_unposed = cfg->num_envs; s->n_inexact = cfg->num_envs;
-    s->fast_ok = false; s->rec_cap = 0; s->smem_fast = 0;
+    s->fast_ok = false; s->xy_exact = false; s->rec_cap = 0; s->smem_fast = 0;
     {
         cudaError_t e1 = cudaMalloc(&s->d_pose, sizeof(double4) * (size_t)cfg->num_envs);
         cudaError_t e2 = cudaMalloc(&s->d_shape_id, sizeof(int) * (size_t)cfg->num_envs);
@@ -355,7 +357,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     CU_TRY(cudaMemset(s->d_shape_id, 0xFF, sizeof(int) * (size_t)s->cfg.num_envs));
     std::fill(s->h_shape_id.begin(), s->h_shape_id.end(), -1);
     s->n_unposed = s->cfg.num_envs; s->n_inexact = s->cfg.num_envs;
-    s->fast_ok = false;
+    s->fast_ok = false; s->xy_exact = true;
     s->h_tabs.assign(n_shapes, ShapeTab{});
     // the lookup kernel serves single-warp envs with <= 1024 cells; rows per agent <= 32 and cells per row record <= 31
     double l_min = l_cell[0];
@@ -382,7 +384,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         int ncols = 0, far_cell = 0; long prev_key = -1; double far_d2 = -1.0;
         for (int c = 0; c < n && ok; ++c) {
             const long ix = std::lround((gx[c] - ox_min) / L), iy = std::lround((gy[c] - oy_min) / L);
-            ok = ix >= 0 && ix < 64 && iy >= 0 && iy < 4096 && std::fabs(gx[c] - (ox_min + ix * L)) <= 1e-9 &&
+            ok = ix >= 0 && ix < 64 && iy >= 0 && iy < 64 && std::fabs(gx[c] - (ox_min + ix * L)) <= 1e-9 &&
                  std::fabs(gy[c] - (oy_min + iy * L)) <= 1e-9 && iy * 64 + ix > prev_key;
             if (!ok) break;
             prev_key = iy * 64 + ix;
@@ -395,6 +397,18 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         }
         if (!ok || far_cell == 0) continue;                          // not a lattice shape: its envs use the general scan
         for (size_t r = 0; r < rowmask.size(); ++r) if (rowmask[r] == 0ull) rowstart[r] = (r ? rowstart[r - 1] : 0);
+        const int nrows = (int)rowmask.size();
+        rowmask.resize(64, 0ull); rowstart.resize(64, (unsigned short)n);
+        // exact column / row coordinates: every cell of column ix has the same x bits, every cell of row iy the same y bits
+        // (true for grids generated like assembly_cfg.py:44-99); otherwise the exact-pose kernel variant is not used
+        std::vector<double> colx(64, 0.0), rowy(64, 0.0);
+        std::vector<char> cset(64, 0), rset(64, 0);
+        for (int c = 0; c < n; ++c) {
+            const long ix = std::lround((gx[c] - ox_min) / L), iy = std::lround((gy[c] - oy_min) / L);
+            if (!cset[ix]) { cset[ix] = 1; colx[ix] = gx[c]; }
+            if (!rset[iy]) { rset[iy] = 1; rowy[iy] = gy[c]; }
+            if (colx[ix] != gx[c] || rowy[iy] != gy[c]) s->xy_exact = false;
+        }
         const double h = 0.5 * L;
         const int nb = (int)std::ceil(2.0 * Q / h);
         if ((size_t)nb * nb > (size_t)4 << 20) continue;             // table would be unreasonably large
@@ -418,7 +432,13 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         CU_TRY(cudaGetLastError());
         s->launches++;
         T.ox_min = ox_min; T.oy_min = oy_min; T.inv_l = 1.0 / L; T.q0 = -Q; T.inv_h = 1.0 / h;
-        T.ncols = ncols; T.nrows = (int)rowmask.size(); T.nb = nb; T.far_cell = far_cell;
+        T.ncols = ncols; T.nrows = nrows; T.nb = nb; T.far_cell = far_cell;
+        double *d_colx = nullptr, *d_rowy = nullptr;
+        CU_TRY(cudaMalloc(&d_colx, sizeof(double) * 64)); s->tab_allocs.push_back(d_colx);
+        CU_TRY(cudaMalloc(&d_rowy, sizeof(double) * 64)); s->tab_allocs.push_back(d_rowy);
+        CU_TRY(cudaMemcpy(d_colx, colx.data(), sizeof(double) * 64, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(d_rowy, rowy.data(), sizeof(double) * 64, cudaMemcpyHostToDevice));
+        T.colx = d_colx; T.rowy = d_rowy;
         T.rowmask = d_rowmask; T.rowstart = d_rowstart; T.bins = d_bins; T.spill = d_spill; T.cells = d_cells;
         ++n_tables;
     }
@@ -484,7 +504,7 @@ int swarm_set_grid_pose(swarm_sim *s, int32_t env0, int32_t count, const int32_t
  * cells (every env's grid matched a library shape), 2 = lookup scan with cells recomputed from the library (every pose exact) */
 int swarm_fast_path(const swarm_sim *s) {
     if (!(s && s->fast_ok && s->split && s->n_unposed == 0)) return 0;
-    return (s->n_inexact == 0 && !getenv("SWARM_NO_EXACT_POSE")) ? 2 : 1;
+    return (s->n_inexact == 0 && s->xy_exact && !getenv("SWARM_NO_EXACT_POSE")) ? 2 : 1;
 }
 
 int swarm_reset(swarm_sim *s, uint64_t seed, uint64_t episode, uint64_t env_offset, const uint8_t *env_mask,
