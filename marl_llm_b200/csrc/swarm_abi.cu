@@ -412,7 +412,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         const double h = 0.5 * L;
         const int nb = (int)std::ceil(2.0 * Q / h);
         if ((size_t)nb * nb > (size_t)4 << 20) continue;             // table would be unreasonably large
-        unsigned long long *d_rowmask = nullptr; unsigned short *d_rowstart = nullptr, *d_spill = nullptr; uint2 *d_bins = nullptr;
+        unsigned short *d_spill = nullptr; uint2 *d_bins = nullptr;
         double2 *d_cells = nullptr;
         std::vector<double2> cells(n);
         for (int c = 0; c < n; ++c) cells[c] = make_double2(gx[c], gy[c]);
@@ -420,26 +420,23 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         CU_TRY(cudaMemcpy(d_cells, cells.data(), sizeof(double2) * n, cudaMemcpyHostToDevice));
         unsigned *d_cursor = nullptr;
         const unsigned spill_cap = (unsigned)nb * nb * 2u;
-        CU_TRY(cudaMalloc(&d_rowmask, sizeof(unsigned long long) * rowmask.size())); s->tab_allocs.push_back(d_rowmask);
-        CU_TRY(cudaMalloc(&d_rowstart, sizeof(unsigned short) * rowstart.size())); s->tab_allocs.push_back(d_rowstart);
         CU_TRY(cudaMalloc(&d_bins, sizeof(uint2) * (size_t)nb * nb)); s->tab_allocs.push_back(d_bins);
         CU_TRY(cudaMalloc(&d_spill, sizeof(unsigned short) * (size_t)spill_cap)); s->tab_allocs.push_back(d_spill);
         CU_TRY(cudaMalloc(&d_cursor, sizeof(unsigned))); s->tab_allocs.push_back(d_cursor);
-        CU_TRY(cudaMemcpy(d_rowmask, rowmask.data(), sizeof(unsigned long long) * rowmask.size(), cudaMemcpyHostToDevice));
-        CU_TRY(cudaMemcpy(d_rowstart, rowstart.data(), sizeof(unsigned short) * rowstart.size(), cudaMemcpyHostToDevice));
         CU_TRY(cudaMemset(d_cursor, 0, sizeof(unsigned)));
         k_build_bins<<<(nb * nb + 127) / 128, 128>>>(s->d_shape_grid + (size_t)k * 2 * ngm, n, -Q, h, nb, d_bins, d_spill, d_cursor, spill_cap);
         CU_TRY(cudaGetLastError());
         s->launches++;
         T.ox_min = ox_min; T.oy_min = oy_min; T.inv_l = 1.0 / L; T.q0 = -Q; T.inv_h = 1.0 / h;
         T.ncols = ncols; T.nrows = nrows; T.nb = nb; T.far_cell = far_cell;
-        double *d_colx = nullptr, *d_rowy = nullptr;
-        CU_TRY(cudaMalloc(&d_colx, sizeof(double) * 64)); s->tab_allocs.push_back(d_colx);
-        CU_TRY(cudaMalloc(&d_rowy, sizeof(double) * 64)); s->tab_allocs.push_back(d_rowy);
-        CU_TRY(cudaMemcpy(d_colx, colx.data(), sizeof(double) * 64, cudaMemcpyHostToDevice));
-        CU_TRY(cudaMemcpy(d_rowy, rowy.data(), sizeof(double) * 64, cudaMemcpyHostToDevice));
-        T.colx = d_colx; T.rowy = d_rowy;
-        T.rowmask = d_rowmask; T.rowstart = d_rowstart; T.bins = d_bins; T.spill = d_spill; T.cells = d_cells;
+        std::vector<unsigned long long> blob(LATTICE_WORDS, 0ull);
+        memcpy(blob.data(), colx.data(), 512); memcpy(blob.data() + 64, rowy.data(), 512);
+        memcpy(blob.data() + 128, rowmask.data(), 512); memcpy(blob.data() + 192, rowstart.data(), 128);
+        unsigned long long *d_blob = nullptr;
+        CU_TRY(cudaMalloc(&d_blob, sizeof(unsigned long long) * LATTICE_WORDS)); s->tab_allocs.push_back(d_blob);
+        CU_TRY(cudaMemcpy(d_blob, blob.data(), sizeof(unsigned long long) * LATTICE_WORDS, cudaMemcpyHostToDevice));
+        T.lattice = d_blob;
+        T.bins = d_bins; T.spill = d_spill; T.cells = d_cells;
         ++n_tables;
     }
     CU_TRY(cudaDeviceSynchronize());

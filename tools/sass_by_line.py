@@ -5,8 +5,11 @@ so, kern = sys.argv[1], sys.argv[2]
 src = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("-") else os.path.join(os.path.dirname(__file__), "..", "marl_llm_b200", "csrc", "swarm_kernels.cuh")
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=d, capture_output=True)
-cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-txt = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout.splitlines()
+txt = []
+for cub in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):
+    t = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout
+    if ("\n" + kern + ":") in t:
+        txt = t.splitlines(); break
 on = False; cur = None; pend = None; cnt = collections.Counter(); seq = []
 for l in txt:
     if l.startswith(kern + ":"): on = True; continue
