@@ -52,7 +52,7 @@ int round32(int n) { return (n + 31) & ~31; }
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1) {
     (void)n_g_pad;
     size_t ring = (size_t)2 * CHUNK_CELLS * sizeof(double2);
-    if (rec_cap >= 0) ring = std::max(ring, (size_t)4 * rec_cap + 128);                            // lookup scan: row records + running counts
+    if (rec_cap >= 0) ring = std::max(ring, (size_t)(nt / 32) * ((size_t)4 * rec_cap + 128));      // lookup scan: per warp, row records + running counts
     size_t b = ring + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
@@ -96,6 +96,16 @@ step_fn_t pick_fast(bool f32, bool emit, bool exact) {
     }
     if (f32) return emit ? (step_fn_t)k_step<float, false, true, 128, 2, 1> : (step_fn_t)k_step<float, false, false, 128, 2, 1>;
     return emit ? (step_fn_t)k_step<double, false, true, 128, 2, 1> : (step_fn_t)k_step<double, false, false, 128, 2, 1>;
+}
+// multi-warp envs (more than 32 agents): the whole step in one launch, with the lookup scan
+template <typename OUT, int FASTV>
+step_fn_t pick_fast_big2(bool dyn, bool emit) {
+    if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, 1024, 0, FASTV> : (step_fn_t)k_step<OUT, true, false, 1024, 0, FASTV>;
+    return emit ? (step_fn_t)k_step<OUT, false, true, 1024, 0, FASTV> : (step_fn_t)k_step<OUT, false, false, 1024, 0, FASTV>;
+}
+step_fn_t pick_fast_big(bool f32, bool dyn, bool emit, bool exact) {
+    if (exact) return f32 ? pick_fast_big2<float, 2>(dyn, emit) : pick_fast_big2<double, 2>(dyn, emit);
+    return f32 ? pick_fast_big2<float, 1>(dyn, emit) : pick_fast_big2<double, 1>(dyn, emit);
 }
 step_fn_t pick_step(bool f32, bool dyn, bool emit, int nt, int phase = 0) {
     if (nt <= 128) {
@@ -363,8 +373,8 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     double l_min = l_cell[0];
     for (int k = 1; k < n_shapes; ++k) l_min = std::min(l_min, l_cell[k]);
     const double rr = s->cfg.d_sen / l_min;
-    const bool eligible = s->nt == 32 && s->K.n_words <= 32 && ngm <= 1023 && rr <= 14.9 && !s->cfg.brute_force_scan &&
-                          !getenv("SWARM_NO_LOOKUP_SCAN");
+    const bool eligible = ((s->split && s->nt == 32) || (!s->split && s->nt > 32)) && s->K.n_words <= 32 && ngm <= 1023 && rr <= 14.9 && !s->cfg.brute_force_scan &&
+                          !getenv("SWARM_NO_LOOKUP_SCAN") && !(s->nt > 32 && getenv("SWARM_NO_LOOKUP_SCAN_BIG"));
     if (!eligible) return SWARM_OK;
     const double half_extent = std::max(s->K.half_w, s->K.half_h);
     // origin-frame positions the table must cover: |p| up to the walls (+ slack: they are soft), |offset| up to half - 1 (ENV:184-185)
@@ -445,13 +455,17 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     CU_TRY(cudaMemcpy(s->d_tabs, s->h_tabs.data(), sizeof(ShapeTab) * n_shapes, cudaMemcpyHostToDevice));
     s->K.shapes = s->d_tabs;
     const int rows_per_agent = (2.0 * (rr + 2e-3) + 2.0 <= 16.0) ? 16 : 32;
-    s->rec_cap = s->nt * rows_per_agent;
+    s->rec_cap = 32 * rows_per_agent;                              // per warp
     s->K.rec_cap = s->rec_cap;
-    s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, s->cfg.emit_indices != 0, s->cfg.num_obs_grid_max, 2, s->rec_cap);
-    for (int f32 = 0; f32 < 2; ++f32)
-        for (int emit = 0; emit < 2; ++emit)
-            for (int exact = 0; exact < 2; ++exact)
-                CU_TRY(raise_smem_limit((const void *)pick_fast(f32 != 0, emit != 0, exact != 0), s->smem_fast));
+    const bool emit = s->cfg.emit_indices != 0, f32 = s->cfg.out_dtype == SWARM_F32;
+    s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, emit, s->cfg.num_obs_grid_max, s->split ? 2 : 0, s->rec_cap);
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, s->cfg.device));
+    if (s->smem_fast > (size_t)prop.sharedMemPerBlockOptin) return SWARM_OK;      // does not fit (e.g. 1024 agents with index arrays): general scan
+    for (int exact = 0; exact < 2; ++exact) {
+        if (s->split) CU_TRY(raise_smem_limit((const void *)pick_fast(f32, emit, exact != 0), s->smem_fast));
+        else for (int dyn = 0; dyn < 2; ++dyn) CU_TRY(raise_smem_limit((const void *)pick_fast_big(f32, dyn != 0, emit, exact != 0), s->smem_fast));
+    }
     s->fast_ok = true;
     return SWARM_OK;
 }
@@ -500,7 +514,7 @@ int swarm_set_grid_pose(swarm_sim *s, int32_t env0, int32_t count, const int32_t
 /* which second-half kernel the next swarm_step / swarm_observe runs: 0 = general culled scan, 1 = lookup scan on the stored
  * cells (every env's grid matched a library shape), 2 = lookup scan with cells recomputed from the library (every pose exact) */
 int swarm_fast_path(const swarm_sim *s) {
-    if (!(s && s->fast_ok && s->split && s->n_unposed == 0)) return 0;
+    if (!(s && s->fast_ok && s->n_unposed == 0)) return 0;
     return (s->n_inexact == 0 && s->xy_exact && !getenv("SWARM_NO_EXACT_POSE")) ? 2 : 1;
 }
 
@@ -655,7 +669,8 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
         else pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
         s->launches += 2;
     } else {
-        pick_step(f32, dyn, emit, s->nt, 0)<<<ctas, s->nt, s->smem, st>>>(K);
+        if (const int fp = swarm_fast_path(s)) pick_fast_big(f32, dyn, emit, fp == 2)<<<ctas, s->nt, s->smem_fast, st>>>(K);
+        else pick_step(f32, dyn, emit, s->nt, 0)<<<ctas, s->nt, s->smem, st>>>(K);
         s->launches++;
     }
     CU_TRY(cudaGetLastError());

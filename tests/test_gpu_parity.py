@@ -36,7 +36,8 @@ def make_sim(E, n_a, n_g_max, r_avoid, **kw):
     if lookup:
         sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
     import os
-    sim.expect_fast = lookup and n_a <= 32 and not kw.get("brute_force_scan", False) and not os.environ.get("SWARM_FUSED_STEP")
+    big_fits = not (kw.get("emit_indices", False) and n_a > 512)     # 1024 agents + index arrays: shared memory is full without the records
+    sim.expect_fast = lookup and big_fits and not kw.get("brute_force_scan", False) and not (n_a <= 32 and os.environ.get("SWARM_FUSED_STEP"))
     return sim
 
 
@@ -443,6 +444,34 @@ def test_large_swarm_1024_agents_matches_oracle():
         sim.step(torch.from_numpy(a).cuda()); ob.step(a)
         compare_all(sim, ob, t)
     assert ob.in_flags.sum() > 100 and (ob.occupied_index >= 0).sum() > 100
+
+
+def test_large_swarm_1024_agents_production_layout():
+    """BASELINE config 4 in the layout the bench times (fp32 outputs, no index arrays): every output the layout has, against
+    the oracle, from a state with a third of each swarm on its shape (in-shape / occupancy / subsample / reward branches).  In
+    the lookup variant this is the multi-warp lookup-scan kernel (32 warps per env, each with its own row records)."""
+    E, n_a = 3, 1024
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=4)
+    rng = np.random.RandomState(13)
+    for e in range(E):
+        idx = rng.choice(grids[e].shape[1], n_a // 3, replace=False)
+        P[e][:, :n_a // 3] = grids[e][:, idx] + rng.normal(0, 0.01, (2, n_a // 3))
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float32, emit_indices=False)
+    ob = orc.OracleBatch(params, nthreads=E)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.obs.fill_(float("nan"))
+    sim.observe(); ob.observe(with_reward=True)
+    assert np.array_equal(sim.obs.cpu().numpy(), ob.obs.astype(np.float32))
+    for t in range(4):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        sim.obs.fill_(float("nan"))
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        for name, got, ref in (("p", sim.p, ob.p), ("dp", sim.dp, ob.dp), ("obs", sim.obs, ob.obs.astype(np.float32)),
+                               ("reward", sim.reward, ob.reward.astype(np.float32)), ("a_prior", sim.a_prior, ob.a_prior.astype(np.float32)),
+                               ("nbr", sim.neighbor_index, ob.neighbor_index), ("in_flags", sim.in_flags, ob.in_flags)):
+            assert np.array_equal(got.cpu().numpy(), ref), (name, t)
+    assert ob.in_flags.sum() > 100
 
 
 def test_periodic_boundaries_batch_vs_oracle():
