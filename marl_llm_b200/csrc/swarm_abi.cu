@@ -55,7 +55,7 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, i
     if (rec_cap >= 0) ring = std::max(ring, (size_t)(nt / 32) * ((size_t)4 * rec_cap + 128));      // lookup scan: per warp, row records + running counts
     size_t b = ring + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
-    b += (size_t)((n_words + 1) & ~1) * 4 + 16;                                                    // covered mask + 2 mbarriers
+    b += (size_t)((n_words + 3) & ~3) * 4 + 16;                                                    // covered mask + 2 mbarriers
     if (phase != 2) {                                                                                // the second-half kernel parks its neighbour list on the idle ring
         b += (size_t)TOPO * nt * sizeof(int);                                                       // neighbour list
         b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
