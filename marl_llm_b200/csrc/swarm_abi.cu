@@ -60,7 +60,7 @@ size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, i
         b += (size_t)TOPO * nt * sizeof(int);                                                       // neighbour list
         b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
     }
-    if (rec_cap >= 0) b += (size_t)64 * (8 + 8 + 8 + 2);                                            // lookup scan: lattice tables of the env's shape
+    if (rec_cap >= 0) b += (size_t)LATTICE_WORDS * 8;                                            // lookup scan: lattice tables of the env's shape
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
     if (nt == 32 && n_words <= 32 && scratch > ring) b += scratch;   // aliases the TMA ring when it fits
     return b;
