@@ -367,18 +367,28 @@ def main():
         barrier()
         return max_over_ranks(ev0.elapsed_time(ev1), device="cuda"), sim.launch_count - l0
 
-    def roofline_of(ms_per_step):
+    def measured_traffic(regime):
+        prof = os.path.join(REPO, "profiles", "traffic.json")
+        try:
+            return json.load(open(prof)).get(f"{args.layout}_{regime}_bytes_per_launch") if n_a == 30 and E == 65536 else None
+        except Exception:
+            return None
+
+    def roofline_of(ms_per_step, regime):
         """HBM for the 30-agent configurations (algorithmic bytes: 1126 B per agent-step in the production
         layout at n_g = 512), the FP32 pipe for the O(n_a^2) large-swarm configuration (6 n_a + 6 n_g flops per agent-step)."""
         if n_a <= 128:
             b = sim.algorithmic_bytes_per_agent_step(survey=True)
             achieved = b * E * n_a / (ms_per_step * 1e-3) / 1e9
             ext = sim.algorithmic_bytes_per_agent_step(survey=False)
-            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(regime),
+                    "algorithmic_bytes_per_launch": b * E * n_a,
                     "peak_source": peak_src, "launch_ms": ms_per_step, "algorithmic_bytes_per_agent_step": b,
                     "bytes_per_agent_step_incl_neighbor_index_and_seed": ext,
                     "frac_incl_neighbor_index_and_seed": ext * E * n_a / (ms_per_step * 1e-3) / 1e9 / peak,
-                    "kernel": "swarm::k_step<PH=1> + swarm::k_step<PH=2> (one step = two launches; the second is the dominant one)"}
+                    "kernel": ("swarm::k_step<PH=1> + swarm::k_step<PH=2, FAST=%d> (one step = two launches; the second, the lookup-scan "
+                               "kernel, is the dominant one)" % sim.fast_path) if sim.fast_path else
+                              "swarm::k_step<PH=1> + swarm::k_step<PH=2> (one step = two launches; the second is the dominant one)"}
         f32, f64 = sim.measure_fma_peak()
         flops = 6.0 * n_a + 6.0 * float(np.mean(shapes["n_g"]))
         achieved = flops * E * n_a / (ms_per_step * 1e-3) / 1e12
@@ -386,7 +396,7 @@ def main():
                 "peak_source": "measured here: register-resident FMA loop (swarm_measure_fma_peak)", "fp64_peak_tflops": f64,
                 "launch_ms": ms_per_step, "algorithmic_flops_per_agent_step": flops,
                 "note": "pair loops run an fp32 filter pass + exact fp64 on the survivors; flops = SURVEY 8(d) count (selection excluded)",
-                "kernel": "swarm::k_step<PH=0, 1024 threads>"}
+                "kernel": "swarm::k_step<PH=0, MAXT=1024, FAST=%d>" % sim.fast_path}
 
     regimes = {}
     sampler = ClockSampler(local_rank); sampler.start()
@@ -408,18 +418,12 @@ def main():
             ms, launches = timed(step_converged, K, W)
         stats = all_reduce_stats(episode_stats(sim.reward, sim.in_flags)).tolist()   # episode statistics (not timed)
         regimes[regime] = {"ms_per_step": ms / K, "value": world * E * n_a * K / (ms * 1e-3), "gpu_launches": int(launches),
-                           "roofline": roofline_of(ms / K),
+                           "roofline": roofline_of(ms / K, regime),
                            "mean_reward": stats[0] / stats[2], "in_shape_fraction": stats[1] / stats[2]}
     clocks = sampler.stop()
     head = regimes[want[0]]
     ms, launches, value, roofline = head["ms_per_step"] * K, head["gpu_launches"], head["value"], head["roofline"]
     bytes_per_launch = sim.algorithmic_bytes_per_agent_step(survey=True) * E * n_a
-    prof = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.isfile(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{args.layout}_{want[0]}_bytes_per_launch")
-        except Exception:
-            pass
 
     # ---- end to end through host buffers ----
     e2e = None
