@@ -107,7 +107,7 @@ typedef struct swarm_config {
     int32_t emit_indices;           /* also write sensed_index / occupied_index every step             */
     int32_t exact_occupancy;        /* debug: always take the per-agent sequential occupancy filter    */
     int32_t brute_force_scan;       /* debug / A-B: evaluate every (agent, cell) pair in the grid scan    */
-    int32_t reserved_;
+    int32_t debug_flags;            /* debug / tests: bit 0 = always evaluate the reward's psi sums in fp64 (skip the fp32 estimate) */
     double d_sen;                   /* 0.4                                             ENV:199          */
     double r_avoid;                 /*                                                 ENV:124          */
     double size_a;                  /* 0.035                                           ENV:44           */
@@ -327,7 +327,9 @@ int swarm_policy_debug_buffer(swarm_policy *p, float *layer1_acc_dev);
 int64_t swarm_policy_launch_count(const swarm_policy *p);
 
 /* gather for a time-indexed ring: next_obs of ring row r is row r + next_row_offset of the OBS array (buf->next_obs may be
- * NULL); next_row_offset < 0 behaves like swarm_rollout_gather. */
+ * NULL); next_row_offset < 0 behaves like swarm_rollout_gather.  Precondition for both gathers: 0 <= rows[k] and
+ * rows[k] + max(next_row_offset, 0) < buf->capacity; a row outside that range is clamped into it by the kernel (never read
+ * out of bounds), so validate indices on the host if a wrong index must be an error. */
 int swarm_rollout_gather_ring(const swarm_rollout_buffers *buf, const int64_t *rows_dev, int32_t n, int64_t next_row_offset, float *obs,
                               float *act, float *reward, float *next_obs, float *done, float *act_prior, float *log_pi, void *stream);
 

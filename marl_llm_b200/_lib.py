@@ -17,7 +17,7 @@ class SwarmConfig(C.Structure):
         ("n_g_max", C.c_int32), ("topo_nei_max", C.c_int32), ("num_obs_grid_max", C.c_int32),
         ("num_occupied_grid_max", C.c_int32), ("is_con_self_state", C.c_int32), ("is_periodic", C.c_int32),
         ("want_prior", C.c_int32), ("out_dtype", C.c_int32), ("emit_indices", C.c_int32),
-        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("reserved_", C.c_int32),
+        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("debug_flags", C.c_int32),
         ("d_sen", C.c_double), ("r_avoid", C.c_double), ("size_a", C.c_double),
         ("k_ball", C.c_double), ("k_wall", C.c_double), ("c_wall", C.c_double),
         ("dt", C.c_double), ("vel_max", C.c_double), ("mass", C.c_double),

@@ -35,7 +35,7 @@ class BatchedAssemblySim:
     def __init__(self, num_envs, n_a, n_g_max, r_avoid, *, device=0, out_dtype=torch.float32, emit_indices=False,
                  want_prior=True, is_con_self_state=True, is_periodic=False, d_sen=0.4, size_a=0.035, k_ball=30.0,
                  k_wall=100.0, c_wall=5.0, dt=0.1, vel_max=0.8, mass=1.0, half_width=2.4, half_height=2.4,
-                 exact_occupancy=False, brute_force_scan=False, guard_bytes=0):
+                 exact_occupancy=False, brute_force_scan=False, exact_reward_sums=False, guard_bytes=0):
         if not torch.cuda.is_available():
             raise SwarmError("BatchedAssemblySim needs a CUDA device; there is no CPU fallback")
         if out_dtype not in (torch.float32, torch.float64):
@@ -57,6 +57,7 @@ class BatchedAssemblySim:
         cfg.out_dtype = _lib.SWARM_F32 if out_dtype == torch.float32 else _lib.SWARM_F64
         cfg.emit_indices, cfg.exact_occupancy = int(emit_indices), int(exact_occupancy)
         cfg.brute_force_scan = int(brute_force_scan)
+        cfg.debug_flags = 1 if exact_reward_sums else 0
         cfg.d_sen, cfg.r_avoid, cfg.size_a = d_sen, r_avoid, size_a
         cfg.k_ball, cfg.k_wall, cfg.c_wall = k_ball, k_wall, c_wall
         cfg.dt, cfg.vel_max, cfg.mass = dt, vel_max, mass

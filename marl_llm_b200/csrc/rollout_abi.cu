@@ -106,7 +106,8 @@ int swarm_rollout_gather_ring(const swarm_rollout_buffers *buf, const int64_t *r
     G.B = to_dev(buf); G.idx = reinterpret_cast<const long *>(rows_dev); G.n = n;
     G.obs = obs; G.act = act; G.rew = reward; G.next_obs = next_obs; G.done = done; G.prior = act_prior; G.log_pi = log_pi;
     G.next_off = (long)next_row_offset;
-    k_rollout_gather<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(G);
+    G.capacity = (long)buf->capacity; G.bad = nullptr;      // rows outside [0, capacity) are clamped by the kernel, never read out of bounds
+    k_rollout_gather<<<(unsigned)(((long)n * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(G);
     RCU_TRY(cudaGetLastError());
     return SWARM_OK;
 }

@@ -191,12 +191,18 @@ struct GatherParams {
     int n;
     float *obs, *act, *rew, *next_obs, *done, *prior, *log_pi;   // [n][dim] outputs; prior / log_pi may be NULL
     long next_off;             // >= 0: next_obs of row r is row r + next_off of the OBS array (time-indexed ring); < 0: the next_obs array
+    long capacity;             // rows of the ring: out-of-range indices are clamped into it (and flagged), never dereferenced
+    int *bad;                  // device flag set when an index was out of range (may be NULL)
 };
 
 __global__ void __launch_bounds__(256) k_rollout_gather(const GatherParams P) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= P.n) return;
-    const long r = P.idx[warp];
+    const long gw = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= P.n) return;
+    const int warp = (int)gw;
+    long r = P.idx[warp];
+    const long hi = P.capacity - 1 - (P.next_off > 0 ? P.next_off : 0);        // last row whose next_obs row is still inside the ring
+    if (r < 0 || r > hi) { if (lane == 0 && P.bad) *P.bad = 1; r = r < 0 ? 0 : (hi < 0 ? 0 : hi); }
     const int D = P.B.obs_dim, A = P.B.act_dim;
     const float *nsrc = P.next_off >= 0 ? P.B.obs + (r + P.next_off) * D : P.B.next_obs + r * D;
     if ((D & 3) == 0) {                                    // rows are 16-byte aligned: vector copies

@@ -231,7 +231,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.E = cfg->num_envs;
     K.p = buf->p; K.dp = buf->dp; K.grid = reinterpret_cast<const double2 *>(buf->grid);
     K.n_g = buf->n_g; K.in_thresh = buf->in_thresh;
-    K.wbox = reinterpret_cast<const float4 *>(buf->word_box); K.frame = buf->frame; K.brute_scan = cfg->brute_force_scan != 0;
+    K.wbox = reinterpret_cast<const float4 *>(buf->word_box); K.frame = buf->frame; K.brute_scan = cfg->brute_force_scan != 0; K.exact_reward = (cfg->debug_flags & 1) != 0;
     K.obs = buf->obs; K.reward = buf->reward;
     K.nbr = buf->neighbor_index; K.in_flags = buf->in_flags; K.nearest = buf->nearest_cell;
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;

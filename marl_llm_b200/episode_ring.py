@@ -15,6 +15,7 @@ the 1.5 GB transposes of a conventional push disappear from the loop; only the l
 replacement: its sampling rule is uniform over the stored rollout, not the reference's window arithmetic."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -80,10 +81,13 @@ class EpisodeRing:
 
     def gather(self, rows, is_prior=False, is_log_pi=False):
         """Transitions at flat ring rows (t * N + n) as the reference's 7-tuple of fp32 CUDA tensors."""
-        idx = torch.as_tensor(rows).to(self.device, torch.int64).contiguous()
+        if not isinstance(rows, torch.Tensor) or not rows.is_cuda:      # host indices: validated on the host, no device sync
+            host = np.asarray(rows)
+            if host.size and (host.min() < 0 or host.max() >= len(self)):
+                raise IndexError("transition out of range")
+            rows = torch.from_numpy(np.ascontiguousarray(host, dtype=np.int64))
+        idx = rows.to(self.device, torch.int64).contiguous()
         n = int(idx.numel())
-        if n and (int(idx.min()) < 0 or int(idx.max()) >= len(self)):
-            raise IndexError("transition out of range")
         o = lambda d: torch.empty(n, d, dtype=torch.float32, device=self.device)   # noqa: E731
         obs, act, rew, nxt, done = o(self.D), o(self.A), o(1), o(self.D), o(1)
         prior, logpi = (o(self.A) if is_prior else None), (o(1) if is_log_pi else None)

@@ -107,10 +107,15 @@ class ReplayBufferAgent:
 
     def gather(self, inds, is_prior=False, is_log_pi=False):
         """Rows `inds` (any integer array / tensor) of every array, as CUDA fp32 tensors (BUF:152-165)."""
-        idx = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(self.device, torch.int64).contiguous()
+        # indices that start on the host are validated there (no device round trip); device tensors are trusted to be in
+        # range — the kernel clamps rows into the ring instead of reading out of bounds (include/swarm_b200.h)
+        if not isinstance(inds, torch.Tensor) or not inds.is_cuda:
+            host = np.asarray(inds)
+            if host.size and (host.min() < 0 or host.max() >= self.total_length):
+                raise IndexError("sample row out of range")
+            inds = torch.from_numpy(np.ascontiguousarray(host, dtype=np.int64))
+        idx = inds.to(self.device, torch.int64).contiguous()
         n = int(idx.numel())
-        if n and (int(idx.min()) < 0 or int(idx.max()) >= self.total_length):
-            raise IndexError("sample row out of range")
         o = lambda d: torch.empty(n, d, dtype=torch.float32, device=self.device)   # noqa: E731
         obs, act, rew, nxt, done = o(self.state_dim), o(self.action_dim), o(1), o(self.state_dim), o(1)
         prior = o(self.action_dim) if is_prior else None

@@ -293,6 +293,35 @@ def test_exact_occupancy_path_equals_shared_mask_path():
     assert (ob.occupied_index >= 0).sum() > 1000
 
 
+def test_reward_estimate_decides_like_the_exact_sums():
+    """The reward predicate |v| < 0.05 (CPP:495-552) is normally decided by an fp32 estimate with an error bound and only
+    falls back to the reference's fp64 psi sums when undecided; `exact_reward_sums` forces the fp64 path for every agent.
+    Both must give the oracle's rewards on a batch where most agents sit inside their shapes for many steps."""
+    E, n_a = 128, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=23)
+    rng = np.random.RandomState(5)
+    for e in range(E):      # start assembled: every agent on a cell of its shape
+        idx = rng.choice(grids[e].shape[1], n_a, replace=False)
+        P[e] = grids[e][:, idx] + rng.normal(0, 0.01, (2, n_a))
+    ngm = int(shapes["n_g"].max())
+    est = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    exact = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True, exact_reward_sums=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(est, ob, params, grids, P, DP); load_batch(exact, ob, params, grids, P, DP)
+    est.observe(); exact.observe(); ob.observe(with_reward=True)
+    assert np.array_equal(est.reward.cpu().numpy(), ob.reward) and np.array_equal(exact.reward.cpu().numpy(), ob.reward)
+    ones = 0
+    for t in range(80):
+        a = goal_seeking_action(ob.obs, ob.dp, rng, noise=0.15)
+        ta = torch.from_numpy(a).cuda()
+        est.step(ta); exact.step(ta); ob.step(a)
+        assert np.array_equal(est.reward.cpu().numpy(), ob.reward), t
+        assert np.array_equal(exact.reward.cpu().numpy(), ob.reward), t
+        assert torch.equal(est.obs, exact.obs)
+        ones += int(ob.reward.sum())
+    assert ob.in_flags.mean() > 0.5 and ones > 1000          # both outcomes of the predicate occurred many times
+
+
 def test_grid_swap_between_steps_like_eval_script():
     """eval_assembly.py:34-57 overwrites env.grid_center / l_cell / n_g between steps; the next step's prior must come
     from the NEW grid and the OLD neighbour list (assembly.py:613-624), the observation from the new grid."""

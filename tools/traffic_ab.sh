@@ -1,4 +1,4 @@
-cd /root/repo
+cd "$(dirname "$0")/.."
 for v in "$@"; do
   SWARM_B200_LIB=$PWD/marl_llm_b200/lib/variants/$v.so ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_step -s 8 -c 2 --csv --log-file gpurun_out/traffic_$v.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > /dev/null 2>&1
   python - "$v" <<'PY'
