@@ -49,18 +49,18 @@ double thresh_le(double h) {
 
 int round32(int n) { return (n + 31) & ~31; }
 
-size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1) {
+size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1, int lat_n = 0) {
     (void)n_g_pad;
     size_t ring = (size_t)2 * CHUNK_CELLS * sizeof(double2);
     if (rec_cap >= 0) ring = std::max(ring, (size_t)(nt / 32) * ((size_t)4 * rec_cap + 128));      // lookup scan: per warp, row records + running counts
-    size_t b = ring + (size_t)n_words * sizeof(float4) + (size_t)4 * nt * sizeof(double);   // TMA ring + word boxes + state tile
+    size_t b = ring + (rec_cap >= 0 ? 0 : (size_t)n_words * sizeof(float4)) + (size_t)(phase == 2 ? 2 : 4) * nt * sizeof(double);   // TMA ring / records + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 3) & ~3) * 4 + 16;                                                    // covered mask + 2 mbarriers
     if (phase != 2) {                                                                                // the second-half kernel parks its neighbour list on the idle ring
         b += (size_t)TOPO * nt * sizeof(int);                                                       // neighbour list
         b += (size_t)nt * sizeof(float2);                                                            // fp32 positions (pair-loop filter)
     }
-    if (rec_cap >= 0) b += (size_t)LATTICE_WORDS * 8;                                            // lookup scan: lattice tables of the env's shape
+    if (rec_cap >= 0) b += (size_t)(3 * lat_n + lat_n / 4) * 8;                                            // lookup scan: lattice tables of the env's shape
     const size_t scratch = (size_t)3 * n_obs * sizeof(double) + 32 * sizeof(int);                   // sparse schedule scratch:
     if (nt == 32 && n_words <= 32 && scratch > ring) b += scratch;   // aliases the TMA ring when it fits
     return b;
@@ -379,7 +379,9 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     const double half_extent = std::max(s->K.half_w, s->K.half_h);
     // origin-frame positions the table must cover: |p| up to the walls (+ slack: they are soft), |offset| up to half - 1 (ENV:184-185)
     const double Q = 1.4142135623730951 * ((half_extent + 0.25) + std::max(half_extent - 1.0, 0.0)) + 0.1;
-    int n_tables = 0;
+    int n_tables = 0, lat_n = 8;
+    struct HostLattice { std::vector<double> colx, rowy; std::vector<unsigned long long> rowmask; std::vector<unsigned short> rowstart; };
+    std::vector<HostLattice> lat(n_shapes);
     for (int k = 0; k < n_shapes; ++k) {
         const double *gx = grids + (size_t)k * 2 * ngm, *gy = gx + n_g[k];
         const int n = n_g[k];
@@ -439,18 +441,26 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
         s->launches++;
         T.ox_min = ox_min; T.oy_min = oy_min; T.inv_l = 1.0 / L; T.q0 = -Q; T.inv_h = 1.0 / h;
         T.ncols = ncols; T.nrows = nrows; T.nb = nb; T.far_cell = far_cell;
-        std::vector<unsigned long long> blob(LATTICE_WORDS, 0ull);
-        memcpy(blob.data(), colx.data(), 512); memcpy(blob.data() + 64, rowy.data(), 512);
-        memcpy(blob.data() + 128, rowmask.data(), 512); memcpy(blob.data() + 192, rowstart.data(), 128);
-        unsigned long long *d_blob = nullptr;
-        CU_TRY(cudaMalloc(&d_blob, sizeof(unsigned long long) * LATTICE_WORDS)); s->tab_allocs.push_back(d_blob);
-        CU_TRY(cudaMemcpy(d_blob, blob.data(), sizeof(unsigned long long) * LATTICE_WORDS, cudaMemcpyHostToDevice));
-        T.lattice = d_blob;
+        lat[k].colx = colx; lat[k].rowy = rowy; lat[k].rowmask = rowmask; lat[k].rowstart = rowstart;
+        lat_n = std::max(lat_n, (std::max(ncols, nrows) + 7) & ~7);
         T.bins = d_bins; T.spill = d_spill; T.cells = d_cells;
         ++n_tables;
     }
     CU_TRY(cudaDeviceSynchronize());
     if (n_tables == 0) return SWARM_OK;
+    // lattice blobs, all with lat_n entries per table (see ShapeTab::lattice)
+    for (int k = 0; k < n_shapes; ++k) {
+        if (!s->h_tabs[k].nb) continue;
+        const int words = 3 * lat_n + lat_n / 4;
+        std::vector<unsigned long long> blob(words, 0ull);
+        memcpy(blob.data(), lat[k].colx.data(), 8 * lat_n); memcpy(blob.data() + lat_n, lat[k].rowy.data(), 8 * lat_n);
+        memcpy(blob.data() + 2 * lat_n, lat[k].rowmask.data(), 8 * lat_n); memcpy(blob.data() + 3 * lat_n, lat[k].rowstart.data(), 2 * lat_n);
+        unsigned long long *d_blob = nullptr;
+        CU_TRY(cudaMalloc(&d_blob, sizeof(unsigned long long) * words)); s->tab_allocs.push_back(d_blob);
+        CU_TRY(cudaMemcpy(d_blob, blob.data(), sizeof(unsigned long long) * words, cudaMemcpyHostToDevice));
+        s->h_tabs[k].lattice = d_blob;
+    }
+    s->K.lat_n = lat_n;
     CU_TRY(cudaMalloc(&s->d_tabs, sizeof(ShapeTab) * n_shapes));
     CU_TRY(cudaMemcpy(s->d_tabs, s->h_tabs.data(), sizeof(ShapeTab) * n_shapes, cudaMemcpyHostToDevice));
     s->K.shapes = s->d_tabs;
@@ -458,7 +468,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     s->rec_cap = 32 * rows_per_agent;                              // per warp
     s->K.rec_cap = s->rec_cap;
     const bool emit = s->cfg.emit_indices != 0, f32 = s->cfg.out_dtype == SWARM_F32;
-    s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, emit, s->cfg.num_obs_grid_max, s->split ? 2 : 0, s->rec_cap);
+    s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, emit, s->cfg.num_obs_grid_max, s->split ? 2 : 0, s->rec_cap, lat_n);
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, s->cfg.device));
     if (s->smem_fast > (size_t)prop.sharedMemPerBlockOptin) return SWARM_OK;      // does not fit (e.g. 1024 agents with index arrays): general scan
