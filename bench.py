@@ -184,7 +184,7 @@ def port_rollouts(orc, shapes, n_a, threads, envs, steps):
     return dict(value=envs * steps * n_a / dt, envs=envs, seconds=dt)
 
 
-def widened_path_numbers(torch, sim, act, hbm_peak):
+def widened_path_numbers(torch, sim, act, hbm_peak, shapes):
     """Device-timed numbers of the rows built next to the step path: k_rollout_push against the HBM roofline,
     the policy MLP (fp32 exact path and tcgen05 fp16 path), and the rollout loop policy -> step -> push with nothing on the host."""
     import torch.nn as nn
@@ -246,6 +246,34 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
         state["t"] += 1
         obs_pair[0], obs_pair[1] = spare, prev
     ring_ms = timed(ring_step, 20)
+    # the same loop with an agent-major simulator writing straight into the ring slots (no observation copy at all)
+    direct_ms = None
+    try:
+        from marl_llm_b200.batched import BatchedAssemblySim
+        del ring
+        sim2 = BatchedAssemblySim(E, n_a, sim.n_g_max, sim.r_avoid, device=sim.device.index, obs_layout="agent_major")
+        sim2.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+        sim2.reset(seed=226)
+        ring2 = EpisodeRing(8, E, n_a, D, A)      # the wrap copies slot T back to slot 0: once per 8 steps, inside the timed loop
+        ring2.begin_direct(sim2)
+        st2 = {"t": 0}
+
+        def direct_step():
+            if st2["t"] == ring2.T:
+                ring2.slot_env(0).copy_(ring2.slot_env(ring2.T)); sim2.set_obs_buffer(ring2.slot_env(0)); ring2.begin(); st2["t"] = 0
+            t = st2["t"]
+            _, lp = pol.step(ring2.slot_env(t), explore=True, out=act2, agent_major=True)
+            sim2.set_obs_buffer(ring2.slot_env(t + 1))
+            _, rew, done, _, prior = sim2.step(act2)
+            ring2.record(t, act2, rew, done, prior, lp)
+            st2["t"] = t + 1
+        direct_ms = timed(direct_step, 20)
+        pol_am_ms = timed(lambda: pol.step(ring2.slot_env(0), explore=True, out=act2, want_log_pi=False, agent_major=True), 20)
+        step_am_ms = timed(lambda: sim2.step(act2), 20)
+        del sim2, ring2
+    except Exception as ex:
+        direct_ms = None; pol_am_ms = step_am_ms = None
+        direct_err = f"{type(ex).__name__}: {ex}"
     flop = 2.0 * rows * (D * H + 2 * H * H + H * A)
     return {
         "rollout_push": {"kernel": "swarm::k_rollout_push_tma", "ms": push_ms, "GBps": push_bytes / push_ms / 1e6,
@@ -258,6 +286,10 @@ def widened_path_numbers(torch, sim, act, hbm_peak):
                                 "agent_steps_per_s": rows / loop_ms * 1e3},
         "device_rollout_loop_ring": {"stages": "policy(f16_tc, writes the replay rows) -> step -> small-array push (time-indexed ring)",
                                      "ms_per_step": ring_ms, "agent_steps_per_s": rows / ring_ms * 1e3},
+        "device_rollout_loop_direct": ({"stages": "agent-major simulator writes obs straight into the ring slot; policy(f16_tc) reads contiguous rows; small-array push",
+                                        "ms_per_step": direct_ms, "agent_steps_per_s": rows / direct_ms * 1e3,
+                                        "policy_f16_tc_ms": pol_am_ms, "policy_TFLOPs": flop / pol_am_ms / 1e9, "step_ms": step_am_ms}
+                                       if direct_ms else {"error": direct_err}),
     }
 
 
@@ -484,7 +516,7 @@ def main():
     extras = None
     if rank == 0 and world == 1 and not args.no_extras and not parity and n_a == 30:
         try:
-            extras = widened_path_numbers(torch, sim, acts[0], peak)
+            extras = widened_path_numbers(torch, sim, acts[0], peak, shapes)
         except Exception as ex:            # the widened-path numbers must never cost the main line
             extras = {"error": f"{type(ex).__name__}: {ex}"}
 

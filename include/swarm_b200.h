@@ -88,6 +88,7 @@ enum {
 };
 
 enum { SWARM_F64 = 0, SWARM_F32 = 1 };
+enum { SWARM_OBS_REFERENCE = 0, SWARM_OBS_AGENT_MAJOR = 1 };
 
 /* Everything ENV:27-81,93-138,193-199 fixes per env class; per-env quantities (n_g, l_cell, grid) are set
  * with swarm_set_grid(). */
@@ -108,6 +109,10 @@ typedef struct swarm_config {
     int32_t exact_occupancy;        /* debug: always take the per-agent sequential occupancy filter    */
     int32_t brute_force_scan;       /* debug / A-B: evaluate every (agent, cell) pair in the grid scan    */
     int32_t debug_flags;            /* debug / tests: bit 0 = always evaluate the reward's psi sums in fp64 (skip the fp32 estimate) */
+    int32_t obs_layout;             /* SWARM_OBS_REFERENCE: obs [E][obs_dim][n_a] (CPP:324-328, what env.step returns);
+                                       SWARM_OBS_AGENT_MAJOR: obs [E][n_a][obs_dim], one contiguous row per agent — for consumers on
+                                       the device (swarm_policy_step with obs_agent_major, a replay ring slot); same values    */
+    int32_t reserved_;
     double d_sen;                   /* 0.4                                             ENV:199          */
     double r_avoid;                 /*                                                 ENV:124          */
     double size_a;                  /* 0.035                                           ENV:44           */
@@ -336,6 +341,11 @@ int swarm_rollout_gather_ring(const swarm_rollout_buffers *buf, const int64_t *r
 /* While non-NULL, swarm_policy_step also writes every agent's observation as one fp32 row, rows_dev [E*n_a][obs_dim] (device):
  * the transposition a replay push would do, for free, from the registers of the threads that read the observation anyway. */
 int swarm_policy_rows_out(swarm_policy *p, float *rows_dev);
+
+/* agent_major != 0: the obs pointer of the following swarm_policy_step calls is agent-major, [E*n_a][obs_dim] — the output of a
+ * simulator created with SWARM_OBS_AGENT_MAJOR (each loader thread then reads 128 contiguous bytes instead of 32 strided words),
+ * e.g. a slot of a time-indexed replay ring the simulator wrote its observation into directly. */
+int swarm_policy_obs_layout(swarm_policy *p, int agent_major);
 
 const char *swarm_last_error(void);
 int swarm_abi_version(void);

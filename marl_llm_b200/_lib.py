@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(PKG, "lib", "libswar
 
 SWARM_OK, SWARM_ERR_INVALID, SWARM_ERR_UNSUPPORTED, SWARM_ERR_CUDA, SWARM_ERR_NO_DEVICE = range(5)
 SWARM_F64, SWARM_F32 = 0, 1
+SWARM_OBS_REFERENCE, SWARM_OBS_AGENT_MAJOR = 0, 1
 SWARM_STRATEGY_RULE, SWARM_STRATEGY_LLM = 1, 2
 
 
@@ -17,7 +18,7 @@ class SwarmConfig(C.Structure):
         ("n_g_max", C.c_int32), ("topo_nei_max", C.c_int32), ("num_obs_grid_max", C.c_int32),
         ("num_occupied_grid_max", C.c_int32), ("is_con_self_state", C.c_int32), ("is_periodic", C.c_int32),
         ("want_prior", C.c_int32), ("out_dtype", C.c_int32), ("emit_indices", C.c_int32),
-        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("debug_flags", C.c_int32),
+        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("debug_flags", C.c_int32), ("obs_layout", C.c_int32), ("reserved_", C.c_int32),
         ("d_sen", C.c_double), ("r_avoid", C.c_double), ("size_a", C.c_double),
         ("k_ball", C.c_double), ("k_wall", C.c_double), ("c_wall", C.c_double),
         ("dt", C.c_double), ("vel_max", C.c_double), ("mass", C.c_double),
@@ -47,7 +48,7 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather", "swarm_rollout_push_parts", "swarm_rollout_gather_ring"]
 SWARM_PUSH_OBS, SWARM_PUSH_NEXT_OBS, SWARM_PUSH_SMALL = 1, 2, 4
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
-                  "swarm_policy_set_precision", "swarm_policy_debug_buffer", "swarm_policy_rows_out"]
+                  "swarm_policy_set_precision", "swarm_policy_debug_buffer", "swarm_policy_rows_out", "swarm_policy_obs_layout"]
 SWARM_POLICY_FP32, SWARM_POLICY_F16_TC, SWARM_POLICY_F16X3_TC = 0, 1, 2
 
 
@@ -111,6 +112,7 @@ def load():
                                              C.c_void_p, C.c_int, C.c_void_p]
     lib.swarm_rollout_gather_ring.argtypes = [C.POINTER(SwarmRolloutBuffers), C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 8
     lib.swarm_policy_rows_out.argtypes = [C.c_void_p, C.c_void_p]
+    lib.swarm_policy_obs_layout.argtypes = [C.c_void_p, C.c_int]
     lib.swarm_policy_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
     lib.swarm_policy_destroy.argtypes = [C.c_void_p]
     lib.swarm_policy_load.argtypes = [C.c_void_p] + [C.c_void_p] * 8

@@ -35,7 +35,7 @@ class BatchedAssemblySim:
     def __init__(self, num_envs, n_a, n_g_max, r_avoid, *, device=0, out_dtype=torch.float32, emit_indices=False,
                  want_prior=True, is_con_self_state=True, is_periodic=False, d_sen=0.4, size_a=0.035, k_ball=30.0,
                  k_wall=100.0, c_wall=5.0, dt=0.1, vel_max=0.8, mass=1.0, half_width=2.4, half_height=2.4,
-                 exact_occupancy=False, brute_force_scan=False, exact_reward_sums=False, guard_bytes=0):
+                 exact_occupancy=False, brute_force_scan=False, exact_reward_sums=False, obs_layout="reference", guard_bytes=0):
         if not torch.cuda.is_available():
             raise SwarmError("BatchedAssemblySim needs a CUDA device; there is no CPU fallback")
         if out_dtype not in (torch.float32, torch.float64):
@@ -58,6 +58,8 @@ class BatchedAssemblySim:
         cfg.emit_indices, cfg.exact_occupancy = int(emit_indices), int(exact_occupancy)
         cfg.brute_force_scan = int(brute_force_scan)
         cfg.debug_flags = 1 if exact_reward_sums else 0
+        cfg.obs_layout = {"reference": _lib.SWARM_OBS_REFERENCE, "agent_major": _lib.SWARM_OBS_AGENT_MAJOR}[obs_layout]
+        self.obs_layout = obs_layout
         cfg.d_sen, cfg.r_avoid, cfg.size_a = d_sen, r_avoid, size_a
         cfg.k_ball, cfg.k_wall, cfg.c_wall = k_ball, k_wall, c_wall
         cfg.dt, cfg.vel_max, cfg.mass = dt, vel_max, mass
@@ -89,7 +91,8 @@ class BatchedAssemblySim:
         self._word_box = z(E, self.n_g_pad // 32, 4, dtype=torch.float32)    # acceleration data of the culled grid scan
         self._frame = z(E, 2, dtype=torch.float64)
         self.nearest_cell = z(E, n, dtype=torch.int32)
-        self.obs = z(E, self.obs_dim, n, dtype=out_dtype)
+        # obs: the reference's [E, obs_dim, n_a], or [E, n_a, obs_dim] (agent-major rows, for device-side consumers)
+        self.obs = z(E, self.obs_dim, n, dtype=out_dtype) if obs_layout == "reference" else z(E, n, self.obs_dim, dtype=out_dtype)
         self.reward = z(E, 1, n, dtype=out_dtype)
         self.done = z(E, 1, n, dtype=torch.bool)
         self._a_prior = [z(E, 2, n, dtype=out_dtype), z(E, 2, n, dtype=out_dtype)]

@@ -30,6 +30,7 @@ struct swarm_policy {
     int n_sm;
     float *debug;        // test hook: layer-1 accumulators of the tensor-core path
     float *rows_out;     // optional agent-major copy of the observations (swarm_policy_rows_out)
+    int obs_am;          // the observations passed to swarm_policy_step are agent-major rows (swarm_policy_obs_layout)
     bool loaded;
     int64_t launches;
 };
@@ -47,7 +48,7 @@ int swarm_policy_create(int32_t device, int32_t obs_dim, int32_t hidden_dim, int
     PCU_TRY(cudaSetDevice(device));
     swarm_policy *p = new swarm_policy();
     p->device = device; p->obs_dim = obs_dim; p->hidden = hidden_dim; p->act_dim = act_dim; p->loaded = false; p->launches = 0;
-    p->precision = SWARM_POLICY_FP32; p->debug = nullptr; p->rows_out = nullptr; p->d_w16 = nullptr; p->d_w16x = nullptr;
+    p->precision = SWARM_POLICY_FP32; p->debug = nullptr; p->rows_out = nullptr; p->obs_am = 0; p->d_w16 = nullptr; p->d_w16x = nullptr;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
         delete p;
@@ -135,7 +136,7 @@ int swarm_policy_step(swarm_policy *p, const float *obs, int32_t num_envs, int32
     if (num_envs <= 0 || n_a <= 0 || explore < 0 || explore > 2) return pfail(SWARM_ERR_INVALID, "bad argument");
     PCU_TRY(cudaSetDevice(p->device));
     PolicyParams P;
-    P.obs = obs; P.act = act; P.log_pi = log_pi; P.rows_out = p->rows_out;
+    P.obs = obs; P.act = act; P.log_pi = log_pi; P.rows_out = p->rows_out; P.obs_am = p->obs_am;
     P.n_cols = (long)num_envs * n_a; P.n_a = n_a; P.K0 = p->obs_dim; P.A = p->act_dim;
     for (int l = 0; l < 3; ++l) {
         P.Wt[l] = p->d_w + (size_t)l * POL_HP * POL_HP;
@@ -179,6 +180,12 @@ int swarm_policy_set_precision(swarm_policy *p, int precision) {
     if (precision != SWARM_POLICY_FP32 && p->act_dim > TC_AMAX)
         return pfail(SWARM_ERR_UNSUPPORTED, "the tensor-core policy path supports act_dim <= 4 (shared-memory budget)");
     p->precision = precision;
+    return SWARM_OK;
+}
+
+int swarm_policy_obs_layout(swarm_policy *p, int agent_major) {
+    if (!p) return swarm_set_last_error_(SWARM_ERR_INVALID, "null policy");
+    p->obs_am = agent_major ? 1 : 0;
     return SWARM_OK;
 }
 

@@ -28,6 +28,7 @@ constexpr int POL_AMAX = 8;      // largest action dimension
 struct PolicyParams {
     const float *obs; float *act; float *log_pi;        // log_pi [E][1][n_a] or NULL
     float *rows_out;             // optional [E*n_a][K0]: every agent's observation as one row (replay storage for free), or NULL
+    int obs_am;                  // obs is agent-major [E*n_a][K0] (k_step with SWARM_OBS_AGENT_MAJOR) instead of [E][K0][n_a]
     long n_cols;                 // E * n_a
     int n_a, K0, A;              // agents per env, observation features (<= POL_HP), action dimension (<= POL_AMAX)
     const float *Wt[3];          // [POL_HP][POL_HP] transposed weights Wt[k][n] of the three hidden layers, zero-padded
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(POL_THREADS, 1) k_policy_mlp(const PolicyParam
         float v = 0.f;
         if (k < P.K0 && col < P.n_cols) {
             const long e = col / n_a; const int a = (int)(col - e * n_a);
-            v = P.obs[(e * P.K0 + k) * n_a + a];
+            v = P.obs_am ? P.obs[col * P.K0 + k] : P.obs[(e * P.K0 + k) * n_a + a];
             if (P.rows_out) P.rows_out[col * P.K0 + k] = v;
         }
         hA[idx] = v;
@@ -339,10 +340,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
 #pragma unroll 1
             for (int c = 0; c < FPL / 32; ++c) {                         // 32 loads in flight per thread and batch (register budget: 512 threads)
                 float f[32];
+                if (P.obs_am && (P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
+                    // agent-major observations: this thread's 32 features are 128 contiguous bytes of the agent's row
+                    const float4 *r4 = reinterpret_cast<const float4 *>(P.obs + col * (long)P.K0 + k_lo + c * 32);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int k = k_lo + c * 32 + q;
-                    f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = valid ? __ldg(r4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = k_lo + c * 32 + q;
+                        f[q] = (valid && k < P.K0) ? __ldg(P.obs_am ? P.obs + col * (long)P.K0 + k : orow + (long)k * n_a) : 0.f;
+                    }
                 }
                 if (ROWS && valid) {                                // the row chunk this thread holds: 128 contiguous bytes
                     float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;
@@ -596,10 +607,20 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTc
 #pragma unroll 1
             for (int c = 0; c < FPL / 32; ++c) {
                 float f[32];
+                if (P.obs_am && (P.K0 & 3) == 0 && k_lo + c * 32 + 32 <= P.K0) {
+                    // agent-major observations: this thread's 32 features are 128 contiguous bytes of the agent's row
+                    const float4 *r4 = reinterpret_cast<const float4 *>(P.obs + col * (long)P.K0 + k_lo + c * 32);
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int k = k_lo + c * 32 + q;
-                    f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 v = valid ? __ldg(r4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = k_lo + c * 32 + q;
+                        f[q] = (valid && k < P.K0) ? __ldg(P.obs_am ? P.obs + col * (long)P.K0 + k : orow + (long)k * n_a) : 0.f;
+                    }
                 }
                 if (ROWS && valid) {
                     float *rw = P.rows_out + col * P.K0 + k_lo + c * 32;

@@ -49,11 +49,16 @@ double thresh_le(double h) {
 
 int round32(int n) { return (n + 31) & ~31; }
 
+#ifdef SWARM_PH2_VEL_GLOBAL
+constexpr bool vel_global = true;
+#else
+constexpr bool vel_global = false;
+#endif
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1, int lat_n = 0) {
     (void)n_g_pad;
     size_t ring = (size_t)2 * CHUNK_CELLS * sizeof(double2);
     if (rec_cap >= 0) ring = std::max(ring, (size_t)(nt / 32) * ((size_t)4 * rec_cap + 128));      // lookup scan: per warp, row records + running counts
-    size_t b = ring + (rec_cap >= 0 ? 0 : (size_t)n_words * sizeof(float4)) + (size_t)(phase == 2 ? 2 : 4) * nt * sizeof(double);   // TMA ring / records + word boxes + state tile
+    size_t b = ring + (rec_cap >= 0 ? 0 : (size_t)n_words * sizeof(float4)) + (size_t)(vel_global && phase == 2 ? 2 : 4) * nt * sizeof(double);   // TMA ring / records + word boxes + state tile
     b += (size_t)n_words * nt * 4 * (emit ? 2 : 1);
     b += (size_t)((n_words + 3) & ~3) * 4 + 16;                                                    // covered mask + 2 mbarriers
     if (phase != 2) {                                                                                // the second-half kernel parks its neighbour list on the idle ring
@@ -186,7 +191,7 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
 /* shared with the other translation units of the library */
 int swarm_set_last_error_(int code, const char *msg) { return fail(code, msg); }
 
-int swarm_abi_version(void) { return 1; }
+int swarm_abi_version(void) { return 2; }
 /* host-only helper exposed for tests: the squared-distance threshold equivalent to sqrt(s) < d (le=0) or <= d (le=1) */
 double swarm_sqrt_threshold(double d, int le) { return le ? thresh_le(d) : thresh_lt(d); }
 const char *swarm_last_error(void) { return g_last_error.c_str(); }
@@ -204,6 +209,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     if (cfg->n_a > 1024) return fail(SWARM_ERR_UNSUPPORTED, "n_a > 1024 not supported by the fused kernel");
     if (cfg->num_obs_grid_max < 2 || cfg->num_occupied_grid_max < 2) return fail(SWARM_ERR_INVALID, "list caps must be >= 2");
     if (cfg->out_dtype != SWARM_F64 && cfg->out_dtype != SWARM_F32) return fail(SWARM_ERR_INVALID, "bad out_dtype");
+    if (cfg->obs_layout != SWARM_OBS_REFERENCE && cfg->obs_layout != SWARM_OBS_AGENT_MAJOR) return fail(SWARM_ERR_INVALID, "bad obs_layout");
     if (!buf->p || !buf->dp || !buf->grid || !buf->n_g || !buf->in_thresh || !buf->obs || !buf->reward ||
         !buf->a_prior[0] || !buf->a_prior[1] || !buf->neighbor_index || !buf->in_flags || !buf->word_box || !buf->frame ||
         !buf->nearest_cell)
@@ -231,7 +237,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     K.E = cfg->num_envs;
     K.p = buf->p; K.dp = buf->dp; K.grid = reinterpret_cast<const double2 *>(buf->grid);
     K.n_g = buf->n_g; K.in_thresh = buf->in_thresh;
-    K.wbox = reinterpret_cast<const float4 *>(buf->word_box); K.frame = buf->frame; K.brute_scan = cfg->brute_force_scan != 0; K.exact_reward = (cfg->debug_flags & 1) != 0;
+    K.wbox = reinterpret_cast<const float4 *>(buf->word_box); K.frame = buf->frame; K.brute_scan = cfg->brute_force_scan != 0; K.exact_reward = (cfg->debug_flags & 1) != 0; K.obs_am = cfg->obs_layout == SWARM_OBS_AGENT_MAJOR;
     K.obs = buf->obs; K.reward = buf->reward;
     K.nbr = buf->neighbor_index; K.in_flags = buf->in_flags; K.nearest = buf->nearest_cell;
     K.sensed = buf->sensed_index; K.occupied = buf->occupied_index;
@@ -469,6 +475,7 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     s->K.rec_cap = s->rec_cap;
     const bool emit = s->cfg.emit_indices != 0, f32 = s->cfg.out_dtype == SWARM_F32;
     s->smem_fast = step_smem_bytes(s->nt, s->K.n_g_pad, s->K.n_words, emit, s->cfg.num_obs_grid_max, s->split ? 2 : 0, s->rec_cap, lat_n);
+    if (const char *x = getenv("SWARM_DEBUG_EXTRA_SMEM_FAST")) s->smem_fast += (size_t)atoi(x);   // occupancy experiments only
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, s->cfg.device));
     if (s->smem_fast > (size_t)prop.sharedMemPerBlockOptin) return SWARM_OK;      // does not fit (e.g. 1024 agents with index arrays): general scan

@@ -54,6 +54,20 @@ class EpisodeRing:
         """[N, obs_dim] view of observation slot t: hand it to DevicePolicy.step(rows_out=...)."""
         return self.obs_ring[t]
 
+    def slot_env(self, t):
+        """[E, n_a, obs_dim] view of slot t: the observation buffer of an agent-major simulator (`sim.set_obs_buffer`)."""
+        return self.obs_ring[t].view(self.E, self.n_a, self.D)
+
+    def begin_direct(self, sim):
+        """Start a rollout in which an agent-major simulator writes its observations straight into the slots: its current
+        observation is copied into slot 0 once and slot 0 becomes its observation buffer."""
+        assert sim.obs_layout == "agent_major" and sim.out_dtype == torch.float32
+        self.begin()
+        s0 = self.slot_env(0)
+        if sim.obs.data_ptr() != s0.data_ptr():
+            s0.copy_(sim.obs)
+            sim.set_obs_buffer(s0)
+
     def record(self, t, act, rew, done, act_prior=None, log_pi=None):
         """Small per-agent arrays of step t, from the simulator's layouts ([E, dim, n_a]); one launch, no observation traffic."""
         assert t == self.filled and t < self.T, (t, self.filled, self.T)

@@ -66,14 +66,19 @@ class DevicePolicy:
     def scale_noise(self, scale):                       # agents.py:60-67
         self.scale = float(scale)
 
-    def step(self, obs, explore=False, out=None, want_log_pi=True, rows_out=None):
-        """agents.py:69-96.  Returns (action, log_pi): [E, act_dim, n_a], [E, 1, n_a] (leading axis dropped for 2-D input)."""
+    def step(self, obs, explore=False, out=None, want_log_pi=True, rows_out=None, agent_major=False):
+        """agents.py:69-96.  Returns (action, log_pi): [E, act_dim, n_a], [E, 1, n_a] (leading axis dropped for 2-D input).
+        agent_major=True: obs is [E, n_a, obs_dim] (a simulator created with obs_layout='agent_major', or a replay-ring slot)."""
         if not (isinstance(obs, torch.Tensor) and obs.is_cuda and obs.dtype == torch.float32):
             raise TypeError("DevicePolicy.step takes the simulator's fp32 CUDA observation tensor")
         squeeze = obs.dim() == 2
         o = (obs.unsqueeze(0) if squeeze else obs).contiguous()
-        E, D, n_a = o.shape
+        if agent_major:
+            E, n_a, D = o.shape
+        else:
+            E, D, n_a = o.shape
         assert D == self.obs_dim
+        check(self.lib.swarm_policy_obs_layout(self._h, int(bool(agent_major))), "swarm_policy_obs_layout")
         act = out if out is not None else torch.empty(E, self.act_dim, n_a, dtype=torch.float32, device=self.device)
         assert act.is_contiguous() and act.numel() == E * self.act_dim * n_a and act.dtype == torch.float32
         log_pi = torch.empty(E, 1, n_a, dtype=torch.float32, device=self.device) if want_log_pi else None

@@ -49,3 +49,21 @@ def rollout_ring(sim, policy, ring, steps, explore=True):
         obs_prev, spare = next_obs, obs_prev
     ring.close(obs_prev)
     return mean_rew
+
+
+def rollout_ring_direct(sim, policy, ring, steps, explore=True):
+    """The ring loop with an agent-major simulator (`obs_layout='agent_major'`): the simulator writes the observation of step
+    t + 1 straight into ring slot t + 1 (`set_obs_buffer`), the policy reads slot t as contiguous 768-byte rows — no
+    observation is copied or transposed anywhere in the loop.  The simulator's current observation must already be in slot 0
+    (`ring.begin_direct(sim)` does that).  Returns the per-step mean reward ([steps] float64 CUDA tensor)."""
+    assert steps <= ring.T and sim.out_dtype == torch.float32 and sim.obs_layout == "agent_major"
+    act = torch.empty(sim.E, policy.act_dim, sim.n_a, dtype=torch.float32, device=sim.device)
+    mean_rew = torch.zeros(steps, dtype=torch.float64, device=sim.device)
+    for t in range(steps):
+        _, log_pi = policy.step(ring.slot_env(t), explore=explore, out=act, agent_major=True)
+        sim.set_obs_buffer(ring.slot_env(t + 1))
+        _, rew, done, _, prior = sim.step(act)
+        ring.record(t, act, rew, done, prior, log_pi)
+        mean_rew[t] = rew.double().mean()
+    ring.closed = True                     # slot `steps` already holds the last observation
+    return mean_rew

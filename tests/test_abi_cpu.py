@@ -45,7 +45,7 @@ def test_legacy_alias_name_exists():
 
 
 def test_struct_sizes_and_abi_version(lib):
-    assert lib.swarm_abi_version() == 1
+    assert lib.swarm_abi_version() == 2
     cfg = _lib.SwarmConfig()
     cfg.struct_size = C.sizeof(_lib.SwarmConfig)
     cfg.is_con_self_state, cfg.num_obs_grid_max = 1, 80

@@ -322,6 +322,36 @@ def test_reward_estimate_decides_like_the_exact_sums():
     assert ob.in_flags.mean() > 0.5 and ones > 1000          # both outcomes of the predicate occurred many times
 
 
+@pytest.mark.parametrize("n_a,E,emit,dt", [(30, 64, False, torch.float32), (30, 32, True, torch.float64), (100, 8, False, torch.float32), (7, 16, False, torch.float32)])
+def test_agent_major_layout_is_the_transposed_reference_layout(n_a, E, emit, dt):
+    """obs_layout='agent_major' ([E, n_a, obs_dim]: one contiguous row per agent, for device-side consumers) holds exactly the
+    values of the reference layout [E, obs_dim, n_a] (CPP:324-328), every step; everything else is unaffected.  The buffer is
+    poisoned before every step (zero-fill + scattered emission use different address arithmetic in this layout)."""
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=60 + n_a)
+    ngm = int(shapes["n_g"].max())
+    ref = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit)
+    am = make_sim(E, n_a, ngm, r_avoid, out_dtype=dt, emit_indices=emit, obs_layout="agent_major")
+    assert am.obs.shape == (E, n_a, ref.obs_dim)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(ref, ob, params, grids, P, DP); load_batch(am, ob, params, grids, P, DP)
+    am.obs.fill_(float("nan"))
+    ref.observe(); am.observe(); ob.observe()
+    assert torch.equal(am.obs, ref.obs.transpose(1, 2))
+    rng = np.random.RandomState(3)
+    for t in range(70):
+        a = goal_seeking_action(ob.obs, ob.dp, rng) if t % 3 else rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        ta = torch.from_numpy(a).cuda()
+        am.obs.fill_(float("nan"))
+        ref.step(ta); am.step(ta); ob.step(a)
+        assert torch.equal(am.obs, ref.obs.transpose(1, 2)), t
+        assert np.array_equal(ref.obs.cpu().numpy(), ob.obs.astype(np.float64 if emit else np.float32)), t
+        for name in ("p", "dp", "reward", "a_prior", "neighbor_index", "in_flags"):
+            assert torch.equal(getattr(am, name), getattr(ref, name)), (name, t)
+        if emit:
+            assert torch.equal(am.sensed_index, ref.sensed_index) and torch.equal(am.occupied_index, ref.occupied_index)
+    assert ob.in_flags.sum() > 0
+
+
 def test_grid_swap_between_steps_like_eval_script():
     """eval_assembly.py:34-57 overwrites env.grid_center / l_cell / n_g between steps; the next step's prior must come
     from the NEW grid and the OLD neighbour list (assembly.py:613-624), the observation from the new grid."""

@@ -163,3 +163,24 @@ def test_tensor_core_path_rejects_wide_actions():
     pol = DevicePolicy(192, 6, 180)
     with pytest.raises(SwarmError):
         pol.set_precision("f16_tc")
+
+
+@pytest.mark.parametrize("prec,atol", [("fp32", 0.0), ("f16x3_tc", 0.0), ("f16_tc", 0.0)])
+def test_agent_major_observations_give_identical_actions(prec, atol):
+    """swarm_policy_obs_layout: the same observations as agent-major rows [E, n_a, obs_dim] (what an agent-major simulator or
+    a replay-ring slot holds) must give bit-identical actions for every policy kernel — only the loaders' addresses differ."""
+    import torch.nn as nn
+    from marl_llm_b200.policy import DevicePolicy
+    E, n_a, D = 67, 30, 192
+    torch.manual_seed(1)
+    sd = {}
+    for name, (o, i) in (("fc1", (180, D)), ("fc2", (180, 180)), ("fc3", (180, 180)), ("fc4", (2, 180))):
+        l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
+    pol = DevicePolicy(D, 2, 180, precision=prec).load_state_dict(sd)
+    obs = torch.randn(E, D, n_a, device="cuda")
+    a_ref, _ = pol.step(obs)
+    a_ref = a_ref.clone()
+    a_am, _ = pol.step(obs.transpose(1, 2).contiguous(), agent_major=True)
+    assert torch.equal(a_ref, a_am)
+    a_back, _ = pol.step(obs)                       # the layout switch is per call
+    assert torch.equal(a_ref, a_back)

@@ -130,8 +130,9 @@ def test_time_indexed_ring_equals_the_conventional_buffer(prec):
     for name, (o, i) in (("fc1", (180, 192)), ("fc2", (180, 180)), ("fc3", (180, 180)), ("fc4", (2, 180))):
         l = nn.Linear(i, o); sd[name + ".weight"] = l.weight; sd[name + ".bias"] = l.bias
     outs = []
-    for kind in ("buffer", "ring"):
-        sim = BatchedAssemblySim(E, n_a, int(shapes["n_g"].max()), r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"]))
+    for kind in ("buffer", "ring", "direct"):
+        sim = BatchedAssemblySim(E, n_a, int(shapes["n_g"].max()), r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"]),
+                                 obs_layout="agent_major" if kind == "direct" else "reference")
         sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
         sim.reset(seed=8)
         pol = DevicePolicy(192, 2, 180, noise_scale=0.3, seed=5, precision=prec).load_state_dict(sd)
@@ -139,6 +140,14 @@ def test_time_indexed_ring_equals_the_conventional_buffer(prec):
             store = ReplayBufferAgent(T, n, slice(0, n_a), 192, 2)
             rollout(sim, pol, store, T)
             outs.append(store.gather(np.arange(T * n), is_prior=True, is_log_pi=True))
+        elif kind == "direct":
+            # agent-major simulator: it writes every observation straight into the ring slot the policy reads next
+            from marl_llm_b200.rollout_loop import rollout_ring_direct
+            ring = EpisodeRing(T, E, n_a, 192, 2)
+            ring.begin_direct(sim)
+            rollout_ring_direct(sim, pol, ring, T)
+            assert len(ring) == T * n and ring.closed
+            outs.append(ring.gather(np.arange(T * n), is_prior=True, is_log_pi=True))
         else:
             ring = EpisodeRing(T, E, n_a, 192, 2)
             assert len(ring) == 0
@@ -149,5 +158,5 @@ def test_time_indexed_ring_equals_the_conventional_buffer(prec):
             assert smp[0].shape == (64, 192) and smp[5].shape == (64, 2) and smp[6] is None
             with pytest.raises(IndexError):
                 ring.gather([T * n])
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    for a, b, c in zip(*outs):
+        assert torch.equal(a, b) and torch.equal(a, c)
