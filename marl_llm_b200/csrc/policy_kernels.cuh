@@ -348,11 +348,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_policy_mlp_tc(const PolicyTcP
                         const float4 v = valid ? __ldg(r4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
                     }
+                } else if (P.obs_am) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = k_lo + c * 32 + q;
+                        f[q] = (valid && k < P.K0) ? __ldg(P.obs + col * (long)P.K0 + k) : 0.f;
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         const int k = k_lo + c * 32 + q;
-                        f[q] = (valid && k < P.K0) ? __ldg(P.obs_am ? P.obs + col * (long)P.K0 + k : orow + (long)k * n_a) : 0.f;
+                        f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                     }
                 }
                 if (ROWS && valid) {                                // the row chunk this thread holds: 128 contiguous bytes
@@ -615,11 +621,17 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_policy_mlp_tc3(const PolicyTc
                         const float4 v = valid ? __ldg(r4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
                     }
+                } else if (P.obs_am) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int k = k_lo + c * 32 + q;
+                        f[q] = (valid && k < P.K0) ? __ldg(P.obs + col * (long)P.K0 + k) : 0.f;
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
                         const int k = k_lo + c * 32 + q;
-                        f[q] = (valid && k < P.K0) ? __ldg(P.obs_am ? P.obs + col * (long)P.K0 + k : orow + (long)k * n_a) : 0.f;
+                        f[q] = (valid && k < P.K0) ? __ldg(orow + (long)k * n_a) : 0.f;
                     }
                 }
                 if (ROWS && valid) {

@@ -181,6 +181,9 @@ struct swarm_sim {
     bool fast_ok;           // the shapes / sizes allow the lookup kernel at all
     bool xy_exact;          // every library shape has bit-identical x per lattice column and y per lattice row
     int rec_cap; size_t smem_fast;
+    // chunked step: the two halves of a step are different kernels (issue bound / latency bound); chunks of the batch alternate
+    // between two internal streams so that the first half of one chunk overlaps the second half of another
+    cudaStream_t side[2]; cudaEvent_t ev_fork, ev_join[2]; int n_chunks;
 };
 
 extern "C" {
@@ -275,6 +278,22 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
         }
     }
     s->K.pose = s->d_pose; s->K.shape_id = s->d_shape_id;
+    s->side[0] = s->side[1] = nullptr; s->ev_fork = nullptr; s->ev_join[0] = s->ev_join[1] = nullptr;
+    s->n_chunks = 1;
+    if (s->split && cfg->num_envs >= 8192) {
+        // opt-in (SWARM_STEP_CHUNKS=2): measured 0.670 -> 0.663 ms per step with 2 chunks, 0.703 with 4, 0.817 with 8
+        // (profiles/r2_experiments.md) — not worth a fork/join on the caller's stream by default
+        int nc = 1;
+        if (const char *x = getenv("SWARM_STEP_CHUNKS")) nc = std::max(1, std::min(16, atoi(x)));
+        if (nc > 1) {
+            bool ok = cudaStreamCreateWithFlags(&s->side[0], cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaStreamCreateWithFlags(&s->side[1], cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&s->ev_join[0], cudaEventDisableTiming) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&s->ev_join[1], cudaEventDisableTiming) == cudaSuccess;
+            if (ok) s->n_chunks = nc; else cudaGetLastError();
+        }
+    }
     *out = s;
     return SWARM_OK;
 }
@@ -290,6 +309,8 @@ int swarm_destroy(swarm_sim *s) {
     if (s->d_pose) cudaFree(s->d_pose);
     if (s->d_shape_id) cudaFree(s->d_shape_id);
     if (s->d_tabs) cudaFree(s->d_tabs);
+    for (int k = 0; k < 2; ++k) { if (s->side[k]) cudaStreamDestroy(s->side[k]); if (s->ev_join[k]) cudaEventDestroy(s->ev_join[k]); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     for (void *q : s->tab_allocs) cudaFree(q);
     delete s;
     return SWARM_OK;
@@ -681,10 +702,30 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     const int ctas = env_list ? count : s->cfg.num_envs;
     const bool f32 = s->cfg.out_dtype == SWARM_F32, emit = s->cfg.emit_indices != 0;
     if (s->split) {
-        pick_step(f32, dyn, emit, s->nt, 1)<<<ctas, s->nt, s->smem, st>>>(K);
-        if (const int fp = swarm_fast_path(s)) pick_fast(f32, emit, fp == 2)<<<ctas, s->nt, s->smem_fast, st>>>(K);
-        else pick_step(f32, dyn, emit, s->nt, 2)<<<ctas, s->nt, s->smem2, st>>>(K);
-        s->launches += 2;
+        const int fp = swarm_fast_path(s);
+        step_fn_t k1 = pick_step(f32, dyn, emit, s->nt, 1);
+        step_fn_t k2 = fp ? pick_fast(f32, emit, fp == 2) : pick_step(f32, dyn, emit, s->nt, 2);
+        const size_t sm2 = fp ? s->smem_fast : s->smem2;
+        if (!env_list && s->n_chunks > 1) {
+            // fork: both side streams wait for the caller's stream; chunk c runs on side stream c % 2 (first half, then second
+            // half: same stream, so in order); join: the caller's stream waits for both
+            CU_TRY(cudaEventRecord(s->ev_fork, st));
+            for (int k = 0; k < 2; ++k) CU_TRY(cudaStreamWaitEvent(s->side[k], s->ev_fork, 0));
+            const int per = (ctas + s->n_chunks - 1) / s->n_chunks;
+            for (int c = 0; c < s->n_chunks; ++c) {
+                K.env0 = c * per;
+                const int n = std::min(per, ctas - K.env0);
+                if (n <= 0) break;
+                k1<<<n, s->nt, s->smem, s->side[c & 1]>>>(K);
+                k2<<<n, s->nt, sm2, s->side[c & 1]>>>(K);
+                s->launches += 2;
+            }
+            for (int k = 0; k < 2; ++k) { CU_TRY(cudaEventRecord(s->ev_join[k], s->side[k])); CU_TRY(cudaStreamWaitEvent(st, s->ev_join[k], 0)); }
+        } else {
+            k1<<<ctas, s->nt, s->smem, st>>>(K);
+            k2<<<ctas, s->nt, sm2, st>>>(K);
+            s->launches += 2;
+        }
     } else {
         if (const int fp = swarm_fast_path(s)) pick_fast_big(f32, dyn, emit, fp == 2)<<<ctas, s->nt, s->smem_fast, st>>>(K);
         else pick_step(f32, dyn, emit, s->nt, 0)<<<ctas, s->nt, s->smem, st>>>(K);
