@@ -89,6 +89,7 @@ enum {
 
 enum { SWARM_F64 = 0, SWARM_F32 = 1 };
 enum { SWARM_OBS_REFERENCE = 0, SWARM_OBS_AGENT_MAJOR = 1 };
+enum { SWARM_VARIANT_ASSEMBLY = 0, SWARM_VARIANT_FLOCKING = 1 };
 
 /* Everything ENV:27-81,93-138,193-199 fixes per env class; per-env quantities (n_g, l_cell, grid) are set
  * with swarm_set_grid(). */
@@ -112,7 +113,7 @@ typedef struct swarm_config {
     int32_t obs_layout;             /* SWARM_OBS_REFERENCE: obs [E][obs_dim][n_a] (CPP:324-328, what env.step returns);
                                        SWARM_OBS_AGENT_MAJOR: obs [E][n_a][obs_dim], one contiguous row per agent — for consumers on
                                        the device (swarm_policy_step with obs_agent_major, a replay ring slot); same values    */
-    int32_t reserved_;
+    int32_t variant;                /* SWARM_VARIANT_ASSEMBLY (the reference env) or SWARM_VARIANT_FLOCKING (VARIANTS.md 3)      */
     double d_sen;                   /* 0.4                                             ENV:199          */
     double r_avoid;                 /*                                                 ENV:124          */
     double size_a;                  /* 0.035                                           ENV:44           */
@@ -227,6 +228,15 @@ int swarm_mark_state_dirty(swarm_sim *sim);
  * (ENV:613-624 uses the neighbor_index of the last _get_obs call).  swarm_is_observed: 1 once an observation exists. */
 int swarm_restore_observation(swarm_sim *sim);
 int swarm_is_observed(const swarm_sim *sim);
+
+/* ---- FlockingSwarm variant (VARIANTS.md 3).  The reference registers `FlockingSwarm-v0` (cus_gym/gym/envs/__init__.py:7-12) but
+ * ships no source for it, so this is a SPECIFIED variant with no oracle (parity unpinned).  A handle created with
+ * variant = SWARM_VARIANT_FLOCKING (n_a <= 128) has obs [E][4 * (6 + is_con_self_state)][n_a] = the assembly observation's head rows
+ * (CPP:102-126); the grid buffers are unused (tiny dummies are fine).  swarm_flock_step = the assembly step's pair phase, walls /
+ * periodic wrap, integrator, k-NN and head rows (the SAME first-half kernel, ENV:442-457, 631-652, CPP:628-698, 775-807, 835-846)
+ * followed by the Reynolds reward of VARIANTS.md 3 into `reward` of the handle; swarm_flock_observe = the same without dynamics. */
+int swarm_flock_observe(swarm_sim *sim, void *stream);
+int swarm_flock_step(swarm_sim *sim, const void *act, int act_dtype, void *stream);
 
 /* reset() tail, ENV:221 -> _get_obs: observation (+ reward) of the current state, no dynamics. */
 int swarm_observe(swarm_sim *sim, void *stream);

@@ -9,6 +9,7 @@ LIB_PATH = os.environ.get("SWARM_B200_LIB") or os.path.join(PKG, "lib", "libswar
 SWARM_OK, SWARM_ERR_INVALID, SWARM_ERR_UNSUPPORTED, SWARM_ERR_CUDA, SWARM_ERR_NO_DEVICE = range(5)
 SWARM_F64, SWARM_F32 = 0, 1
 SWARM_OBS_REFERENCE, SWARM_OBS_AGENT_MAJOR = 0, 1
+SWARM_VARIANT_ASSEMBLY, SWARM_VARIANT_FLOCKING = 0, 1
 SWARM_STRATEGY_RULE, SWARM_STRATEGY_LLM = 1, 2
 
 
@@ -18,7 +19,7 @@ class SwarmConfig(C.Structure):
         ("n_g_max", C.c_int32), ("topo_nei_max", C.c_int32), ("num_obs_grid_max", C.c_int32),
         ("num_occupied_grid_max", C.c_int32), ("is_con_self_state", C.c_int32), ("is_periodic", C.c_int32),
         ("want_prior", C.c_int32), ("out_dtype", C.c_int32), ("emit_indices", C.c_int32),
-        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("debug_flags", C.c_int32), ("obs_layout", C.c_int32), ("reserved_", C.c_int32),
+        ("exact_occupancy", C.c_int32), ("brute_force_scan", C.c_int32), ("debug_flags", C.c_int32), ("obs_layout", C.c_int32), ("variant", C.c_int32),
         ("d_sen", C.c_double), ("r_avoid", C.c_double), ("size_a", C.c_double),
         ("k_ball", C.c_double), ("k_wall", C.c_double), ("c_wall", C.c_double),
         ("dt", C.c_double), ("vel_max", C.c_double), ("mass", C.c_double),
@@ -44,7 +45,7 @@ BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_des
                    "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer", "swarm_strategy_actions",
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
-                   "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho", "swarm_restore_observation", "swarm_is_observed", "swarm_reset_envs", "swarm_measure_fma_peak", "swarm_fast_path", "swarm_set_grid_pose"]
+                   "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho", "swarm_restore_observation", "swarm_is_observed", "swarm_reset_envs", "swarm_measure_fma_peak", "swarm_fast_path", "swarm_set_grid_pose", "swarm_flock_observe", "swarm_flock_step"]
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather", "swarm_rollout_push_parts", "swarm_rollout_gather_ring"]
 SWARM_PUSH_OBS, SWARM_PUSH_NEXT_OBS, SWARM_PUSH_SMALL = 1, 2, 4
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
@@ -86,6 +87,8 @@ def load():
     lib.swarm_set_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_mark_state_dirty.argtypes = [C.c_void_p]
     lib.swarm_fast_path.argtypes = [C.c_void_p]
+    lib.swarm_flock_observe.argtypes = [C.c_void_p, C.c_void_p]
+    lib.swarm_flock_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.swarm_set_grid_pose.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.swarm_restore_observation.argtypes = [C.c_void_p]
     lib.swarm_is_observed.argtypes = [C.c_void_p]

@@ -200,6 +200,7 @@ double swarm_sqrt_threshold(double d, int le) { return le ? thresh_le(d) : thres
 const char *swarm_last_error(void) { return g_last_error.c_str(); }
 int32_t swarm_grid_pad(int32_t n_g_max) { return round32(n_g_max); }
 int32_t swarm_obs_dim(const swarm_config *cfg) {
+    if (cfg->variant == SWARM_VARIANT_FLOCKING) return 2 * 2 * (TOPO + (cfg->is_con_self_state ? 1 : 0));   // head rows only (VARIANTS.md 3)
     return 2 * 2 * (TOPO + 1 + (cfg->is_con_self_state ? 1 : 0)) + 2 * cfg->num_obs_grid_max;
 }
 
@@ -213,6 +214,9 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     if (cfg->num_obs_grid_max < 2 || cfg->num_occupied_grid_max < 2) return fail(SWARM_ERR_INVALID, "list caps must be >= 2");
     if (cfg->out_dtype != SWARM_F64 && cfg->out_dtype != SWARM_F32) return fail(SWARM_ERR_INVALID, "bad out_dtype");
     if (cfg->obs_layout != SWARM_OBS_REFERENCE && cfg->obs_layout != SWARM_OBS_AGENT_MAJOR) return fail(SWARM_ERR_INVALID, "bad obs_layout");
+    if (cfg->variant != SWARM_VARIANT_ASSEMBLY && cfg->variant != SWARM_VARIANT_FLOCKING) return fail(SWARM_ERR_INVALID, "bad variant");
+    if (cfg->variant == SWARM_VARIANT_FLOCKING && (cfg->n_a > 128 || cfg->emit_indices))
+        return fail(SWARM_ERR_UNSUPPORTED, "the flocking variant supports n_a <= 128 and no index arrays");
     if (!buf->p || !buf->dp || !buf->grid || !buf->n_g || !buf->in_thresh || !buf->obs || !buf->reward ||
         !buf->a_prior[0] || !buf->a_prior[1] || !buf->neighbor_index || !buf->in_flags || !buf->word_box || !buf->frame ||
         !buf->nearest_cell)
@@ -237,6 +241,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
                    cfg->r_avoid, cfg->size_a, cfg->k_ball, cfg->k_wall, cfg->c_wall, cfg->dt, cfg->vel_max,
                    cfg->mass, cfg->boundary_pos);
     KParams &K = s->K;
+    if (cfg->variant == SWARM_VARIANT_FLOCKING) K.obs_dim = swarm_obs_dim(cfg);
     K.E = cfg->num_envs;
     K.p = buf->p; K.dp = buf->dp; K.grid = reinterpret_cast<const double2 *>(buf->grid);
     K.n_g = buf->n_g; K.in_thresh = buf->in_thresh;
@@ -735,8 +740,36 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
     return SWARM_OK;
 }
 
+static int flock_launch(swarm_sim *s, bool dyn, const void *act, int act_dtype, cudaStream_t st) {
+    if (s->cfg.variant != SWARM_VARIANT_FLOCKING) return fail(SWARM_ERR_INVALID, "not a flocking handle (swarm_config.variant)");
+    CU_TRY(cudaSetDevice(s->cfg.device));
+    KParams K = s->K;
+    K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
+    const bool f32 = s->cfg.out_dtype == SWARM_F32;
+    pick_step(f32, dyn, false, 32, 1)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);     // the assembly step's first half, unchanged
+    const double d_ref = 2.0 * s->cfg.r_avoid;
+    if (f32) k_flock_reward<float><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (float *)s->buf.reward);
+    else k_flock_reward<double><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (double *)s->buf.reward);
+    CU_TRY(cudaGetLastError());
+    s->launches += 2;
+    s->observed = true;
+    return SWARM_OK;
+}
+
+int swarm_flock_observe(swarm_sim *s, void *stream) {
+    if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    return flock_launch(s, false, nullptr, SWARM_F32, (cudaStream_t)stream);
+}
+
+int swarm_flock_step(swarm_sim *s, const void *act, int act_dtype, void *stream) {
+    if (!s || !act) return fail(SWARM_ERR_INVALID, "null argument");
+    if (act_dtype != SWARM_F32 && act_dtype != SWARM_F64) return fail(SWARM_ERR_INVALID, "bad act_dtype");
+    return flock_launch(s, true, act, act_dtype, (cudaStream_t)stream);
+}
+
 int swarm_observe(swarm_sim *s, void *stream) {
     if (!s) return fail(SWARM_ERR_INVALID, "null handle");
+    if (s->cfg.variant != SWARM_VARIANT_ASSEMBLY) return fail(SWARM_ERR_INVALID, "flocking handle: use swarm_flock_observe");
     CU_TRY(cudaSetDevice(s->cfg.device));
     int rc = launch_step(s, false, nullptr, SWARM_F32, (cudaStream_t)stream);
     if (rc != SWARM_OK) return rc;
@@ -747,6 +780,7 @@ int swarm_observe(swarm_sim *s, void *stream) {
 int swarm_step(swarm_sim *s, const void *act, int act_dtype, void *stream) {
     if (!s || !act) return fail(SWARM_ERR_INVALID, "null argument");
     if (act_dtype != SWARM_F32 && act_dtype != SWARM_F64) return fail(SWARM_ERR_INVALID, "bad act_dtype");
+    if (s->cfg.variant != SWARM_VARIANT_ASSEMBLY) return fail(SWARM_ERR_INVALID, "flocking handle: use swarm_flock_step");
     if (!s->observed) return fail(SWARM_ERR_INVALID, "swarm_step before swarm_observe (reset)");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaSetDevice(s->cfg.device));
