@@ -293,6 +293,42 @@ def widened_path_numbers(torch, sim, act, hbm_peak, shapes):
     }
 
 
+def flocking_line(args, torch, rank, world, local_rank, barrier, max_over_ranks):
+    """BASELINE config 5 (flocking): the variant specified in VARIANTS.md on the shared pair core.  HBM roofline with its own
+    algorithmic bytes: action 8 + p/dp read + write 64 + obs 28 x 4 + reward 4 + neighbor_index 24 = 212 B per agent-step."""
+    from marl_llm_b200.flocking import BatchedFlockingSim
+    E, n_a, K, W = args.envs_per_gpu, min(args.n_a, 128), args.steps, args.warmup
+    sim = BatchedFlockingSim(E, n_a, device=local_rank)
+    sim.reset(seed=226 + rank)
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    acts = torch.rand(16, E, 2, n_a, device="cuda", generator=g) * 2 - 1
+    for t in range(max(W, 3)):
+        sim.step(acts[t % 16])
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(K):
+        sim.step(acts[t % 16])
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device="cuda")
+    clocks = sampler.stop()
+    peak, peak_src = measured_hbm_peak()
+    b = 8 + 64 + sim.obs_dim * 4 + 4 + 24
+    achieved = b * E * n_a / (ms / K * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * E * n_a * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"flocking variant (VARIANTS.md 3; no reference source: parity unpinned), {n_a} agents x {E} envs per GPU (BASELINE config 5)",
+                       "n_a": n_a, "envs_per_gpu": E, "actions": "U(-1,1), ring of 16 device buffers", "l2": "working set per step >> 126 MB L2"},
+            "clocks": clocks, "gpu_launches": 2 * K, "e2e": None, "cpu_baseline": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_agent_step": b,
+                         "kernel": "swarm::k_step<PH=1> (shared with the assembly env) + swarm::k_flock_reward"}}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -312,6 +348,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the rollout-storage / policy / device-loop measurements")
+    ap.add_argument("--variant", default="assembly", choices=["assembly", "flocking"],
+                    help="flocking: the FlockingSwarm variant of VARIANTS.md (BASELINE config 5; no reference source, no CPU baseline)")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-steps", type=int, default=200)
     ap.add_argument("--ref-envs", type=int, default=256)
@@ -341,6 +379,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.variant == "flocking":
+        flocking_line(args, torch, rank, world, local_rank, barrier, max_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     shapes = load_shapes()
     E, n_a = args.envs_per_gpu, args.n_a
