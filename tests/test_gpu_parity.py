@@ -352,6 +352,28 @@ def test_agent_major_layout_is_the_transposed_reference_layout(n_a, E, emit, dt)
     assert ob.in_flags.sum() > 0
 
 
+def test_agents_far_outside_the_arena_take_the_literal_scan():
+    """The lookup scan's bin table covers the arena plus a margin; a caller can still put agents anywhere (`env.p = ...`).
+    Positions far outside (|p| up to 9) select the literal all-cells scan for those agents (CPP:869-885): same outputs as the
+    oracle, including the walls' spring pulling them back for a few steps."""
+    E, n_a = 32, 30
+    shapes, r_avoid, params, grids, P, DP = build_batch(E, n_a, seed=71)
+    rng = np.random.RandomState(4)
+    P = P.copy()
+    P[:, :, ::3] = rng.uniform(-9, 9, P[:, :, ::3].shape)            # every third agent anywhere in an 18 x 18 square
+    ngm = int(shapes["n_g"].max())
+    sim = make_sim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+    ob = orc.OracleBatch(params, nthreads=8)
+    load_batch(sim, ob, params, grids, P, DP)
+    sim.observe(); ob.observe(with_reward=True)
+    compare_all(sim, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
+    for t in range(12):
+        a = rng.uniform(-1, 1, (E, 2, n_a)).astype(np.float32)
+        sim.step(torch.from_numpy(a).cuda()); ob.step(a)
+        compare_all(sim, ob, t)
+    assert np.abs(ob.p).max() > 3.0
+
+
 def test_grid_swap_between_steps_like_eval_script():
     """eval_assembly.py:34-57 overwrites env.grid_center / l_cell / n_g between steps; the next step's prior must come
     from the NEW grid and the OLD neighbour list (assembly.py:613-624), the observation from the new grid."""
