@@ -867,13 +867,14 @@ int swarm_kernel_geometry(const swarm_sim *s, int32_t *threads_per_cta, int32_t 
 }  // extern "C"
 
 // =====================================================================================================
-// Legacy stateless entry points (HOST pointers).  Scratch device memory comes from a process-wide arena.
+// Legacy stateless entry points (HOST pointers).  Every call stages all its inputs in one pinned host buffer and moves them
+// with ONE cudaMemcpy, runs its kernel(s), and brings all outputs back with ONE cudaMemcpy (the reference makes five such
+// calls per env.step(); ten small synchronous copies per call were most of this path's time).  The packed cell list of the
+// last grid is cached on the device: the reference passes the same grid_center for a whole episode.
 // =====================================================================================================
 namespace {
 
 std::mutex g_legacy_mutex;
-unsigned char *g_arena = nullptr;
-size_t g_arena_cap = 0;
 
 [[noreturn]] void legacy_die(const char *where, const std::string &msg) {
     fprintf(stderr, "[swarm_b200] %s: %s (no CPU fallback exists; aborting)\n", where, msg.c_str());
@@ -885,26 +886,88 @@ size_t g_arena_cap = 0;
         if (err__ != cudaSuccess) legacy_die(where, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
     } while (0)
 
-struct Arena {
-    size_t off = 0;
-    explicit Arena(size_t need, const char *where) {
-        need += 4096;
-        if (need > g_arena_cap) {
-            if (g_arena) LEG_TRY(where, cudaFree(g_arena));
-            g_arena = nullptr; g_arena_cap = 0;
-            LEG_TRY(where, cudaMalloc(&g_arena, need));
-            g_arena_cap = need;
+// Device arena mirrored by a pinned host buffer: in() slots are filled on the host and uploaded together, out() slots are
+// downloaded together and scattered to the caller's arrays.  Inputs first, then scratch / outputs (call order = layout order).
+struct Xfer {
+    static unsigned char *dev, *host; static size_t cap;
+    const char *W; size_t off = 0, in_end = 0, out_begin = 0;
+    struct Out { void *dst; size_t off, bytes; };
+    std::vector<Out> outs;
+    Xfer(size_t need, const char *where) : W(where) {
+        need += 8192;
+        if (need > cap) {
+            if (dev) LEG_TRY(W, cudaFree(dev));
+            if (host) LEG_TRY(W, cudaFreeHost(host));
+            dev = host = nullptr; cap = 0;
+            LEG_TRY(W, cudaMalloc(&dev, need));
+            LEG_TRY(W, cudaHostAlloc(&host, need, cudaHostAllocDefault));
+            cap = need;
         }
     }
-    template <typename T> T *take(size_t count) {
+    template <typename T> T *slot(size_t count) {
         off = (off + 255) & ~(size_t)255;
-        T *ptr = reinterpret_cast<T *>(g_arena + off);
+        T *ptr = reinterpret_cast<T *>(dev + off);
         off += count * sizeof(T);
+        if (off > cap) legacy_die(W, "internal: legacy arena too small");
         return ptr;
     }
+    template <typename T> T *in(const void *src, size_t count) {          // must precede every scratch() / out()
+        T *d = slot<T>(count);
+        memcpy(host + (reinterpret_cast<unsigned char *>(d) - dev), src, count * sizeof(T));
+        in_end = off;
+        return d;
+    }
+    void upload() { if (in_end) LEG_TRY(W, cudaMemcpy(dev, host, in_end, cudaMemcpyHostToDevice)); }
+    template <typename T> T *scratch(size_t count) { return slot<T>(count); }
+    template <typename T> T *out(void *dst, size_t count) {
+        T *d = slot<T>(count);
+        if (outs.empty()) out_begin = reinterpret_cast<unsigned char *>(d) - dev;
+        outs.push_back({dst, (size_t)(reinterpret_cast<unsigned char *>(d) - dev), count * sizeof(T)});
+        return d;
+    }
+    void download() {
+        if (outs.empty()) return;
+        LEG_TRY(W, cudaMemcpy(host + out_begin, dev + out_begin, off - out_begin, cudaMemcpyDeviceToHost));
+        for (const Out &o : outs) memcpy(o.dst, host + o.off, o.bytes);
+    }
 };
+unsigned char *Xfer::dev = nullptr, *Xfer::host = nullptr; size_t Xfer::cap = 0;
 
 size_t al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// packed cell list (+ word boxes, frame, n_g, in-shape threshold) of the most recent grid_center, kept on the device
+struct GridCache {
+    std::vector<double> host; int n_g = -1, n_g_pad = 0; double l_cell = 0.0; size_t cap_cells = 0;
+    unsigned char *block = nullptr;          // [src 2*n_g f64 | cells n_g_pad double2 | boxes | frame | n_g | thr]
+    double *src = nullptr; double2 *cells = nullptr; float4 *box = nullptr; double *frame = nullptr; int *d_ng = nullptr; double *d_thr = nullptr;
+} g_grid;
+
+void legacy_grid(const char *W, const double *grid_center, int n_g, double l_cell) {
+    const int n_g_pad = round32(n_g);
+    const bool same = g_grid.n_g == n_g && g_grid.l_cell == l_cell && memcmp(g_grid.host.data(), grid_center, sizeof(double) * 2 * (size_t)n_g) == 0;
+    if (same) return;
+    if ((size_t)n_g_pad > g_grid.cap_cells) {
+        if (g_grid.block) LEG_TRY(W, cudaFree(g_grid.block));
+        const size_t bytes = al(2 * (size_t)n_g_pad * 8) + al((size_t)n_g_pad * 16) + al((size_t)n_g_pad / 32 * 16) + 4 * 256;
+        LEG_TRY(W, cudaMalloc(&g_grid.block, bytes));
+        g_grid.cap_cells = n_g_pad;
+        unsigned char *q = g_grid.block;
+        g_grid.src = reinterpret_cast<double *>(q); q += al(2 * (size_t)n_g_pad * 8);
+        g_grid.cells = reinterpret_cast<double2 *>(q); q += al((size_t)n_g_pad * 16);
+        g_grid.box = reinterpret_cast<float4 *>(q); q += al((size_t)n_g_pad / 32 * 16);
+        g_grid.frame = reinterpret_cast<double *>(q); q += 256;
+        g_grid.d_ng = reinterpret_cast<int *>(q); q += 256;
+        g_grid.d_thr = reinterpret_cast<double *>(q);
+    }
+    const double thr = in_shape_thresh(l_cell);
+    LEG_TRY(W, cudaMemcpy(g_grid.src, grid_center, sizeof(double) * 2 * (size_t)n_g, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(g_grid.d_ng, &n_g, 4, cudaMemcpyHostToDevice));
+    LEG_TRY(W, cudaMemcpy(g_grid.d_thr, &thr, 8, cudaMemcpyHostToDevice));
+    k_pack_grid<<<1, 128>>>(g_grid.src, 2L * n_g, g_grid.d_ng, n_g_pad, g_grid.cells, g_grid.box, g_grid.frame, PoseArgs{});
+    LEG_TRY(W, cudaGetLastError());
+    g_grid.host.assign(grid_center, grid_center + 2 * (size_t)n_g);
+    g_grid.n_g = n_g; g_grid.n_g_pad = n_g_pad; g_grid.l_cell = l_cell;
+}
 
 }  // namespace
 
@@ -928,36 +991,26 @@ void _get_observation(double *p, double *dp, double *heading, double *obs, doubl
     const int nt = round32(n_a);
     const size_t smem = step_smem_bytes(nt, K.n_g_pad, K.n_words, true, num_obs_grid_max);
     const size_t n_obs = (size_t)K.obs_dim * n_a;
-    Arena A(al(16 * n_a * 8) + al(2 * n_g * 8) + al(K.n_g_pad * 16) + al(K.n_words * 16) + al(16) + al(n_obs * 8) + al(n_a * 8 * 3) + al(n_a * TOPO * 4) +
-            al(n_a * 8) + al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * num_occupied_grid_max * 4) + 16 * 256, W);
-    double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_gsrc = A.take<double>(2 * n_g);
-    double2 *d_grid = A.take<double2>(K.n_g_pad);
-    int *d_ng = A.take<int>(1); double *d_thr = A.take<double>(1);
-    float4 *d_box = A.take<float4>(K.n_words); double *d_frame = A.take<double>(2);
-    double *d_obs = A.take<double>(n_obs), *d_rew = A.take<double>(n_a), *d_prior = A.take<double>(2 * n_a);
-    int *d_nbr = A.take<int>(n_a * TOPO), *d_inf = A.take<int>(n_a), *d_near = A.take<int>(n_a);
-    int *d_sidx = A.take<int>((size_t)n_a * num_obs_grid_max), *d_occ = A.take<int>((size_t)n_a * num_occupied_grid_max);
-    const double thr = in_shape_thresh(l_cell);
-    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_dp, dp, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, K.n_g_pad, d_grid, d_box, d_frame, PoseArgs{});
+    legacy_grid(W, grid_center, n_g, l_cell);
+    Xfer X(al(4 * (size_t)n_a * 8) * 2 + al(n_obs * 8) + al((size_t)n_a * 8 * 3) + al((size_t)n_a * TOPO * 4) + al((size_t)n_a * 8) +
+           al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * num_occupied_grid_max * 4) + 16 * 256, W);
+    double *d_p = X.in<double>(p, 2 * (size_t)n_a), *d_dp = X.in<double>(dp, 2 * (size_t)n_a);
+    X.upload();
+    double *d_rew = X.scratch<double>(n_a), *d_prior = X.scratch<double>(2 * (size_t)n_a);
+    int *d_near = X.scratch<int>(n_a);
+    double *d_obs = X.out<double>(obs, n_obs);
+    int *d_nbr = X.out<int>(neighbor_index, (size_t)n_a * TOPO), *d_inf = X.out<int>(in_flags, n_a);
+    int *d_sidx = X.out<int>(sensed_index, (size_t)n_a * num_obs_grid_max), *d_occ = X.out<int>(occupied_index, (size_t)n_a * num_occupied_grid_max);
     LEG_TRY(W, cudaMemset(d_near, 0, (size_t)n_a * 4));
-    K.wbox = d_box; K.frame = d_frame;
-    K.p = d_p; K.dp = d_dp; K.grid = d_grid; K.n_g = d_ng; K.in_thresh = d_thr;
+    K.wbox = g_grid.box; K.frame = g_grid.frame;
+    K.p = d_p; K.dp = d_dp; K.grid = g_grid.cells; K.n_g = g_grid.d_ng; K.in_thresh = g_grid.d_thr;
     K.obs = d_obs; K.reward = d_rew; K.prior_next = d_prior;
     K.nbr = d_nbr; K.in_flags = d_inf; K.nearest = d_near; K.sensed = d_sidx; K.occupied = d_occ;
     step_fn_t f = pick_step(false, false, true, nt);
     LEG_TRY(W, raise_smem_limit((const void *)f, smem));
     f<<<1, nt, smem>>>(K);
     LEG_TRY(W, cudaGetLastError());
-    LEG_TRY(W, cudaMemcpy(obs, d_obs, n_obs * 8, cudaMemcpyDeviceToHost));
-    LEG_TRY(W, cudaMemcpy(neighbor_index, d_nbr, (size_t)n_a * TOPO * 4, cudaMemcpyDeviceToHost));
-    LEG_TRY(W, cudaMemcpy(in_flags, d_inf, (size_t)n_a * 4, cudaMemcpyDeviceToHost));
-    LEG_TRY(W, cudaMemcpy(sensed_index, d_sidx, (size_t)n_a * num_obs_grid_max * 4, cudaMemcpyDeviceToHost));
-    LEG_TRY(W, cudaMemcpy(occupied_index, d_occ, (size_t)n_a * num_occupied_grid_max * 4, cudaMemcpyDeviceToHost));
+    X.download();
 }
 
 void _get_reward(double *p, double *dp, double *heading, double *act, double *reward, double *boundary_pos,
@@ -966,25 +1019,23 @@ void _get_reward(double *p, double *dp, double *heading, double *act, double *re
                  int num_occupied_grid_max, int n_a, int n_g, int dim, bool *condition, bool *is_collide_b2b,
                  bool *is_collide_b2w, double *coefficients) {
     const char *W = "_get_reward";
-    (void)dp; (void)heading; (void)act; (void)occupied_index; (void)l_cell;
+    (void)dp; (void)heading; (void)act; (void)occupied_index;
     (void)num_occupied_grid_max; (void)is_collide_b2b; (void)is_collide_b2w; (void)coefficients;
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
-    Arena A(al(2 * n_a * 8) + al(2 * (size_t)n_g * 8) + al((size_t)n_a * topo_nei_max * 4) + al(n_a * 4) +
-            al((size_t)n_a * num_obs_grid_max * 4) + al(n_a * 8) + 8 * 256, W);
-    double *d_p = A.take<double>(2 * n_a), *d_g = A.take<double>(2 * (size_t)n_g), *d_r = A.take<double>(n_a);
-    int *d_nbr = A.take<int>((size_t)n_a * topo_nei_max), *d_inf = A.take<int>(n_a);
-    int *d_sidx = A.take<int>((size_t)n_a * num_obs_grid_max);
-    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_g, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_inf, in_flags, (size_t)n_a * 4, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_sidx, sensed_index, (size_t)n_a * num_obs_grid_max * 4, cudaMemcpyHostToDevice));
-    k_legacy_reward<<<(n_a + 127) / 128, 128>>>(d_p, d_g, d_nbr, d_inf, d_sidx, n_a, n_g, topo_nei_max, num_obs_grid_max,
+    legacy_grid(W, grid_center, n_g, l_cell);             // k_legacy_reward reads the [2][n_g] copy kept beside the packed cells
+    Xfer X(al(2 * (size_t)n_a * 8) + al((size_t)n_a * topo_nei_max * 4) + al((size_t)n_a * 4) +
+           al((size_t)n_a * num_obs_grid_max * 4) + al((size_t)n_a * 8) + 8 * 256, W);
+    double *d_p = X.in<double>(p, 2 * (size_t)n_a);
+    int *d_nbr = X.in<int>(neighbor_index, (size_t)n_a * topo_nei_max), *d_inf = X.in<int>(in_flags, n_a);
+    int *d_sidx = X.in<int>(sensed_index, (size_t)n_a * num_obs_grid_max);
+    X.upload();
+    double *d_r = X.out<double>(reward, n_a);
+    k_legacy_reward<<<(n_a + 127) / 128, 128>>>(d_p, g_grid.src, d_nbr, d_inf, d_sidx, n_a, n_g, topo_nei_max, num_obs_grid_max,
                                                d_sen, r_avoid, condition[3], condition[4], condition[0],
                                                (boundary_pos[2] - boundary_pos[0]) / 2.0, (boundary_pos[1] - boundary_pos[3]) / 2.0, d_r);
     LEG_TRY(W, cudaGetLastError());
-    LEG_TRY(W, cudaMemcpy(reward, d_r, (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+    X.download();
 }
 
 void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide_b2b, double *boundary_pos,
@@ -993,34 +1044,30 @@ void _sf_b2b_all(double *p, double *sf_b2b, double *d_b2b_edge, bool *is_collide
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
     const size_t nn = (size_t)n_a * n_a;
-    Arena A(al(2 * n_a * 8) * 2 + al(nn * 8) * 2 + al(nn) + 8 * 256, W);
-    double *d_p = A.take<double>(2 * n_a), *d_sf = A.take<double>(2 * n_a);
-    double *d_e = A.take<double>(nn), *d_c = A.take<double>(nn);
-    unsigned char *d_col = A.take<unsigned char>(nn);
-    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_e, d_b2b_edge, nn * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_c, d_b2b_center, nn * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_col, is_collide_b2b, nn, cudaMemcpyHostToDevice));
+    Xfer X(al(2 * (size_t)n_a * 8) * 2 + al(nn * 8) * 2 + al(nn) + 8 * 256, W);
+    double *d_p = X.in<double>(p, 2 * (size_t)n_a);
+    double *d_e = X.in<double>(d_b2b_edge, nn), *d_c = X.in<double>(d_b2b_center, nn);
+    unsigned char *d_col = X.in<unsigned char>(is_collide_b2b, nn);
+    X.upload();
+    double *d_sf = X.out<double>(sf_b2b, 2 * (size_t)n_a);
     k_legacy_sf_b2b<<<(n_a + 127) / 128, 128>>>(d_p, d_e, d_col, d_c, n_a, k_ball, is_periodic ? 1 : 0,
                                                (boundary_pos[2] - boundary_pos[0]) / 2.0, (boundary_pos[1] - boundary_pos[3]) / 2.0, d_sf);
     LEG_TRY(W, cudaGetLastError());
-    LEG_TRY(W, cudaMemcpy(sf_b2b, d_sf, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+    X.download();
 }
 
 void _get_dist_b2w(double *p, double *r, double *d_b2w, bool *isCollision, int dim, int n_a, double *boundary_pos) {
     const char *W = "_get_dist_b2w";
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
-    Arena A(al(2 * n_a * 8) + al(n_a * 8) + al(4 * n_a * 8) + al(4 * n_a) + al(32) + 8 * 256, W);
-    double *d_p = A.take<double>(2 * n_a), *d_r = A.take<double>(n_a), *d_d = A.take<double>(4 * n_a), *d_bp = A.take<double>(4);
-    unsigned char *d_col = A.take<unsigned char>(4 * n_a);
-    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_r, r, (size_t)n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_bp, boundary_pos, 32, cudaMemcpyHostToDevice));
+    Xfer X(al(2 * (size_t)n_a * 8) + al((size_t)n_a * 8) + al(4 * (size_t)n_a * 8) + al(4 * (size_t)n_a) + al(32) + 8 * 256, W);
+    double *d_p = X.in<double>(p, 2 * (size_t)n_a), *d_r = X.in<double>(r, n_a), *d_bp = X.in<double>(boundary_pos, 4);
+    X.upload();
+    double *d_d = X.out<double>(d_b2w, 4 * (size_t)n_a);
+    unsigned char *d_col = X.out<unsigned char>(isCollision, 4 * (size_t)n_a);
     k_legacy_b2w<<<(n_a + 127) / 128, 128>>>(d_p, d_r, d_bp, n_a, d_d, d_col);
     LEG_TRY(W, cudaGetLastError());
-    LEG_TRY(W, cudaMemcpy(d_b2w, d_d, 4 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
-    LEG_TRY(W, cudaMemcpy(isCollision, d_col, 4 * (size_t)n_a, cudaMemcpyDeviceToHost));
+    X.download();
 }
 
 void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_center, int *neighbor_index, double d_sen,
@@ -1029,26 +1076,16 @@ void calculateActionPrior(double *p, double *dp, double *a_prior, double *grid_c
     (void)d_sen;
     if (dim != 2) legacy_die(W, "only dim == 2 is supported");
     std::lock_guard<std::mutex> lock(g_legacy_mutex);
-    const int n_g_pad = round32(n_g);
-    Arena A(al(2 * n_a * 8) * 3 + al(2 * (size_t)n_g * 8) + al((size_t)n_g_pad * 16) + al((size_t)n_g_pad / 2) + al(16) +
-            al((size_t)n_a * topo_nei_max * 4) + 12 * 256, W);
-    double *d_p = A.take<double>(2 * n_a), *d_dp = A.take<double>(2 * n_a), *d_out = A.take<double>(2 * n_a);
-    double *d_gsrc = A.take<double>(2 * (size_t)n_g);
-    double2 *d_grid = A.take<double2>(n_g_pad);
-    int *d_nbr = A.take<int>((size_t)n_a * topo_nei_max), *d_ng = A.take<int>(1);
-    double *d_thr = A.take<double>(1);
-    float4 *d_box = A.take<float4>(n_g_pad / 32); double *d_frame = A.take<double>(2);
-    const double thr = in_shape_thresh(l_cell);
-    LEG_TRY(W, cudaMemcpy(d_p, p, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_dp, dp, 2 * n_a * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_gsrc, grid_center, 2 * (size_t)n_g * 8, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_nbr, neighbor_index, (size_t)n_a * topo_nei_max * 4, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_ng, &n_g, 4, cudaMemcpyHostToDevice));
-    LEG_TRY(W, cudaMemcpy(d_thr, &thr, 8, cudaMemcpyHostToDevice));
-    k_pack_grid<<<1, 128>>>(d_gsrc, 2L * n_g, d_ng, n_g_pad, d_grid, d_box, d_frame, PoseArgs{});
-    k_prior<double><<<1, n_a < 256 ? round32(n_a) : 256>>>(n_a, topo_nei_max, d_p, d_dp, d_grid, n_g_pad, d_ng, d_thr, d_nbr, r_avoid, d_out);
+    legacy_grid(W, grid_center, n_g, l_cell);
+    Xfer X(al(2 * (size_t)n_a * 8) * 3 + al((size_t)n_a * topo_nei_max * 4) + 12 * 256, W);
+    double *d_p = X.in<double>(p, 2 * (size_t)n_a), *d_dp = X.in<double>(dp, 2 * (size_t)n_a);
+    int *d_nbr = X.in<int>(neighbor_index, (size_t)n_a * topo_nei_max);
+    X.upload();
+    double *d_out = X.out<double>(a_prior, 2 * (size_t)n_a);
+    k_prior<double><<<1, n_a < 256 ? round32(n_a) : 256>>>(n_a, topo_nei_max, d_p, d_dp, g_grid.cells, g_grid.n_g_pad, g_grid.d_ng, g_grid.d_thr,
+                                                           d_nbr, r_avoid, d_out);
     LEG_TRY(W, cudaGetLastError());
-    LEG_TRY(W, cudaMemcpy(a_prior, d_out, 2 * (size_t)n_a * 8, cudaMemcpyDeviceToHost));
+    X.download();
 }
 
 }  // extern "C"
