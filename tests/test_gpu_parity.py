@@ -352,6 +352,74 @@ def test_agent_major_layout_is_the_transposed_reference_layout(n_a, E, emit, dt)
     assert ob.in_flags.sum() > 0
 
 
+def synthetic_shapes():
+    """Lattice shapes that stress the lookup tables: a ring (an agent at its centre has dozens of equidistant nearest cells ->
+    spilled candidate lists), scattered dots (holes inside rows), one long row, a 2-cell shape, a wide block (40 columns)."""
+    L = 0.06
+    def cells(mask):
+        iy, ix = np.nonzero(mask)                                  # row-major order = the numbering of assembly_cfg.py:60-79
+        pts = np.stack([ix * L, iy * L]).astype(np.float64)
+        return np.ascontiguousarray(pts - pts.mean(axis=1, keepdims=True))
+    yy, xx = np.mgrid[0:33, 0:33]
+    r = np.hypot(xx - 16, yy - 16)
+    rng = np.random.RandomState(0)
+    out = [cells((r > 11.5) & (r < 13.5)), cells(rng.rand(30, 30) < 0.25), cells(np.ones((1, 50), bool)),
+           cells(np.array([[1, 0, 0, 1]], bool)), cells(np.ones((12, 40), bool))]
+    return out, [L] * len(out)
+
+
+@pytest.mark.parametrize("n_a", [30, 64])
+def test_lookup_scan_on_synthetic_lattice_shapes(n_a):
+    """The lookup scan against the oracle on a shape library built to stress its tables (see synthetic_shapes): poses through
+    set_grid (detected) and set_grid_pose (exact), agents spawned inside, on the rim and around each shape."""
+    from marl_llm_b200.batched import BatchedAssemblySim
+    origins, l_cells = synthetic_shapes()
+    E = 40
+    ngm = max(o.shape[1] for o in origins)
+    r_avoid = 0.2
+    rng = np.random.RandomState(n_a)
+    k = np.arange(E) % len(origins)
+    ang = np.pi * rng.uniform(-1, 1, E)
+    cs, sn, off = np.cos(ang), np.sin(ang), rng.uniform(-1.0, 1.0, (E, 2))
+    grids = [BatchedAssemblySim.grid_from_pose(origins[k[e]], cs[e], sn[e], off[e, 0], off[e, 1]) for e in range(E)]
+    params = [orc.make_params(n_a, grids[e].shape[1], l_cells[k[e]], r_avoid) for e in range(E)]
+    P = np.empty((E, 2, n_a)); DP = rng.uniform(-0.3, 0.3, (E, 2, n_a))
+    for e in range(E):
+        centre = off[e][:, None]
+        P[e] = centre + rng.normal(0, 0.5, (2, n_a))                                   # around / inside the shape
+        pick = rng.choice(grids[e].shape[1], n_a // 3, replace=True)
+        P[e][:, :n_a // 3] = grids[e][:, pick] + rng.normal(0, 0.01, (2, n_a // 3))      # on cells
+        P[e][:, -1] = centre[:, 0]                                                      # exactly at the centre (ring: all cells equidistant-ish)
+    sims = []
+    for mode in ("detected", "exact"):
+        sim = BatchedAssemblySim(E, n_a, ngm, r_avoid, out_dtype=torch.float64, emit_indices=True)
+        sim.set_shapes(origins, l_cells)
+        if mode == "exact":
+            sim.set_grid_pose(k, cs, sn, off[:, 0], off[:, 1])
+        else:
+            blocks, n_g = sim.pack_grids(grids, ngm)
+            sim.set_grid(blocks, n_g, [l_cells[j] for j in k])
+        assert sim.fast_path == (2 if mode == "exact" else 1), (mode, sim.fast_path)
+        sim.set_state(P, DP)
+        sims.append(sim)
+    ob = orc.OracleBatch(params, nthreads=8, ng_max=ngm)
+    for e in range(E):
+        ob.set_grid(e, grids[e])
+    ob.p[:], ob.dp[:] = P, DP
+    for s_ in sims:
+        s_.observe()
+    ob.observe(with_reward=True)
+    for s_ in sims:
+        compare_all(s_, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
+    for t in range(40):
+        a = goal_seeking_action(ob.obs, ob.dp, rng)
+        ob.step(a)
+        for s_ in sims:
+            s_.step(torch.from_numpy(a).cuda())
+            compare_all(s_, ob, t)
+    assert ob.in_flags.sum() > 0 and (ob.sensed_index >= 0).sum() > 1000
+
+
 def test_agents_far_outside_the_arena_take_the_literal_scan():
     """The lookup scan's bin table covers the arena plus a margin; a caller can still put agents anywhere (`env.p = ...`).
     Positions far outside (|p| up to 9) select the literal all-cells scan for those agents (CPP:869-885): same outputs as the
