@@ -352,6 +352,49 @@ def test_agent_major_layout_is_the_transposed_reference_layout(n_a, E, emit, dt)
     assert ob.in_flags.sum() > 0
 
 
+def test_lookup_scan_equals_culled_scan_at_scale():
+    """Two independent algorithms for the second half of the step — the lookup scan (per-shape tables, lattice row records) and
+    the word-box culled scan — on 16 384 envs x 100 steps, half of the envs driven into their shapes: every output identical at
+    every 5th step, and 64 sampled envs follow the oracle."""
+    if SCAN["mode"] != "lookup":
+        pytest.skip("one run is enough: the test builds both kinds of simulator itself")
+    import bench
+    from marl_llm_b200.batched import BatchedAssemblySim
+    E, n_a, steps = 16384, 30, 100
+    shapes = load_shapes()
+    ngm = int(shapes["n_g"].max())
+    r_avoid = orc.r_avoid_for(n_a, shapes["n_g"], shapes["l_cell"])
+    blocks, n_g, l_cell, p, dp = bench.synth_batch(E, n_a, shapes, 13, "random")
+    look = BatchedAssemblySim(E, n_a, ngm, r_avoid)
+    look.set_shapes(shapes["grid_origin"], shapes["l_cell"])
+    cull = BatchedAssemblySim(E, n_a, ngm, r_avoid)
+    for s_ in (look, cull):
+        s_.set_grid(blocks, n_g, l_cell); s_.set_state(p, dp); s_.observe()
+    assert look.fast_path == 1 and cull.fast_path == 0
+    pick = np.arange(0, E, E // 64)
+    ob = orc.OracleBatch([orc.make_params(n_a, int(n_g[e]), float(l_cell[e]), r_avoid) for e in pick], nthreads=16)
+    for k, e in enumerate(pick):
+        ob.set_grid(k, blocks[e, :2 * n_g[e]].reshape(2, n_g[e]))
+    ob.p[:], ob.dp[:] = p[pick], dp[pick]
+    ob.observe()
+    tp = torch.from_numpy(pick).cuda()
+    act = torch.empty(E, 2, n_a, dtype=torch.float32, device="cuda")
+    goal = (torch.arange(E, device="cuda") % 2 == 0)[:, None, None]
+    for t in range(steps):
+        look.fill_actions(act, seed=5, step=t)
+        row = 28
+        a_goal = (3.0 * look.obs[:, row:row + 2, :] - look.dp.float()).clamp(-1, 1)      # noise-free goal seeking from the device obs
+        act = torch.where(goal, a_goal, act).contiguous()
+        look.step(act); cull.step(act)
+        ob.step(act[tp].cpu().numpy())
+        assert np.array_equal(look.obs[tp].cpu().numpy(), ob.obs.astype(np.float32)), t
+        assert np.array_equal(look.reward[tp].cpu().numpy(), ob.reward.astype(np.float32)), t
+        if t % 5 == 4 or t == steps - 1:
+            for name in ("p", "dp", "obs", "reward", "a_prior", "neighbor_index", "in_flags", "nearest_cell"):
+                assert torch.equal(getattr(look, name), getattr(cull, name)), (name, t)
+    assert float(look.in_flags.float().mean()) > 0.2 and float(look.reward.sum()) > 1000
+
+
 def synthetic_shapes():
     """Lattice shapes that stress the lookup tables: a ring (an agent at its centre has dozens of equidistant nearest cells ->
     spilled candidate lists), scattered dots (holes inside rows), one long row, a 2-cell shape, a wide block (40 columns)."""
