@@ -92,6 +92,11 @@ step_fn_t pick2(bool dyn, bool emit) {
     if (dyn) return emit ? (step_fn_t)k_step<OUT, true, true, MAXT, PH> : (step_fn_t)k_step<OUT, true, false, MAXT, PH>;
     return emit ? (step_fn_t)k_step<OUT, false, true, MAXT, PH> : (step_fn_t)k_step<OUT, false, false, MAXT, PH>;
 }
+// first half with a run-time block size (the flocking variant with more than 32 agents)
+step_fn_t pick_first_half_wide(bool f32, bool dyn) {
+    if (f32) return dyn ? (step_fn_t)k_step<float, true, false, 128, 1, 0, true> : (step_fn_t)k_step<float, false, false, 128, 1, 0, true>;
+    return dyn ? (step_fn_t)k_step<double, true, false, 128, 1, 0, true> : (step_fn_t)k_step<double, false, false, 128, 1, 0, true>;
+}
 // second half with the lookup scan (single-warp envs whose grids all have a known pose)
 // (exact: every pose is known exactly -> cells recomputed from the shape library instead of read per env)
 step_fn_t pick_fast(bool f32, bool emit, bool exact) {
@@ -746,7 +751,9 @@ static int flock_launch(swarm_sim *s, bool dyn, const void *act, int act_dtype, 
     KParams K = s->K;
     K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
     const bool f32 = s->cfg.out_dtype == SWARM_F32;
-    pick_step(f32, dyn, false, 32, 1)<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);     // the assembly step's first half, unchanged
+    step_fn_t k1 = s->nt == 32 ? pick_step(f32, dyn, false, 32, 1) : pick_first_half_wide(f32, dyn);   // the assembly step's first half, unchanged
+    CU_TRY(raise_smem_limit((const void *)k1, s->smem));
+    k1<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
     const double d_ref = 2.0 * s->cfg.r_avoid;
     if (f32) k_flock_reward<float><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (float *)s->buf.reward);
     else k_flock_reward<double><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (double *)s->buf.reward);
