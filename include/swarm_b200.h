@@ -199,6 +199,10 @@ int swarm_reset_envs(swarm_sim *sim, uint64_t seed, uint64_t episode, uint64_t e
  * the roofline denominator of the O(n_a^2) large-swarm configuration. */
 int swarm_measure_fma_peak(int32_t device, double *fp32_tflops, double *fp64_tflops);
 
+/* Self-test (tests only): the prior's shared-reciprocal division against the correctly rounded a / b on n pseudo-random operand
+ * pairs; kind 0 = simulator magnitudes, 1 = wide exponents, 2 = divisors 1..6.  *mismatches must come back 0. */
+int swarm_selftest_division(int32_t device, uint64_t n, uint64_t seed, int32_t kind, uint64_t *mismatches);
+
 /* Evaluation metrics of the reference wrapper for every env, on the device: out_dev [E][3] f64 =
  * {coverage_rate, distribution_uniformity, voronoi_based_uniformity} (assembly_wrapper.py:48-72, 74-101, 103-129). */
 int swarm_metrics(swarm_sim *sim, double *out_dev, void *stream);

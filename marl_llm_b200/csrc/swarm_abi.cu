@@ -653,6 +653,22 @@ int swarm_measure_fma_peak(int32_t device, double *fp32_tflops, double *fp64_tfl
     return SWARM_OK;
 }
 
+/* self-test: the shared-reciprocal division of the prior (div_shared) against a / b on n pseudo-random operand pairs */
+int swarm_selftest_division(int32_t device, uint64_t n, uint64_t seed, int32_t kind, uint64_t *mismatches) {
+    if (!mismatches || kind < 0 || kind > 2) return fail(SWARM_ERR_INVALID, "bad argument");
+    CU_TRY(cudaSetDevice(device));
+    unsigned long long *d = nullptr;
+    CU_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
+    k_selftest_division<<<1184, 256>>>((unsigned long long)n, (unsigned long long)seed, kind, d);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CU_TRY(e);
+    *mismatches = h;
+    return SWARM_OK;
+}
+
 int swarm_metrics(swarm_sim *s, double *out_dev, void *stream) {
     if (!s || !out_dev) return fail(SWARM_ERR_INVALID, "null argument");
     CU_TRY(cudaSetDevice(s->cfg.device));

@@ -881,3 +881,15 @@ def test_device_cosine_kernel_matches_libm():
     assert np.all(out[z >= r] == 0.0)
     assert np.max(np.abs(out - want)) <= 2.3e-16, np.max(np.abs(out - want))
     assert np.mean(out == want) > 0.9                       # bit-identical for the vast majority
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_shared_reciprocal_division_is_correctly_rounded(kind):
+    """The prior (CPP:1143-1189) divides two or three numerators by one distance; the second-half kernel shares the reciprocal
+    refinement between them (div_shared).  Every quotient must be the correctly rounded a / b of the reference's plain divisions:
+    2e8 pseudo-random operand pairs per kind (simulator magnitudes, wide exponents, the divisors 1..6 of the velocity mean)."""
+    from marl_llm_b200 import _lib
+    lib = _lib.load()
+    bad = C.c_uint64(123)
+    _lib.check(lib.swarm_selftest_division(0, 200_000_000, 17 + kind, kind, C.byref(bad)), "swarm_selftest_division")
+    assert bad.value == 0
