@@ -501,6 +501,8 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     CU_TRY(cudaMalloc(&s->d_tabs, sizeof(ShapeTab) * n_shapes));
     CU_TRY(cudaMemcpy(s->d_tabs, s->h_tabs.data(), sizeof(ShapeTab) * n_shapes, cudaMemcpyHostToDevice));
     s->K.shapes = s->d_tabs;
+    s->K.n_tab_inline = std::min(n_shapes, (int)TAB_INLINE);
+    for (int k = 0; k < s->K.n_tab_inline; ++k) s->K.tab_inline[k] = s->h_tabs[k];
     const int rows_per_agent = (2.0 * (rr + 2e-3) + 2.0 <= 16.0) ? 16 : 32;
     s->rec_cap = 32 * rows_per_agent;                              // per warp
     s->K.rec_cap = s->rec_cap;
