@@ -329,6 +329,42 @@ def flocking_line(args, torch, rank, world, local_rank, barrier, max_over_ranks)
                          "kernel": "swarm::k_step<PH=1> (shared with the assembly env) + swarm::k_flock_reward"}}), flush=True)
 
 
+def predator_prey_line(args, torch, rank, world, local_rank, barrier, max_over_ranks):
+    """BASELINE config 5 (predator-prey): the variant specified in VARIANTS.md 4, 1/4 pursuers.  HBM roofline with its own algorithmic
+    bytes: action 8 + p/dp read + write 64 + obs 52 x 4 + reward 4 + neighbor_index 48 = 332 B per agent-step."""
+    from marl_llm_b200.predator_prey import BatchedPredatorPreySim
+    E, n, K, W = args.envs_per_gpu, min(args.n_a, 128), args.steps, args.warmup
+    n_p = max(1, n // 4)
+    sim = BatchedPredatorPreySim(E, n_p, n - n_p, device=local_rank)
+    sim.reset(seed=226 + rank)
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    acts = torch.rand(16, E, 2, n, device="cuda", generator=g) * 2 - 1
+    for t in range(max(W, 3)):
+        sim.step(acts[t % 16])
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for t in range(K):
+        sim.step(acts[t % 16])
+    ev1.record()
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device="cuda")
+    clocks = sampler.stop()
+    peak, peak_src = measured_hbm_peak()
+    b = 8 + 64 + sim.obs_dim * 4 + 4 + 48
+    achieved = b * E * n / (ms / K * 1e-3) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * E * n * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"predator-prey variant (VARIANTS.md 4; no reference source: parity unpinned), {n_p} pursuers + {n - n_p} escapers x {E} envs per GPU (BASELINE config 5)",
+                       "n_a": n, "envs_per_gpu": E, "actions": "U(-1,1) for both types, ring of 16 device buffers", "l2": "working set per step >> 126 MB L2"},
+            "clocks": clocks, "gpu_launches": K, "e2e": None, "cpu_baseline": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_agent_step": b, "kernel": "swarm::k_pp_step"}}), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -348,8 +384,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the rollout-storage / policy / device-loop measurements")
-    ap.add_argument("--variant", default="assembly", choices=["assembly", "flocking"],
-                    help="flocking: the FlockingSwarm variant of VARIANTS.md (BASELINE config 5; no reference source, no CPU baseline)")
+    ap.add_argument("--variant", default="assembly", choices=["assembly", "flocking", "predator_prey"],
+                    help="flocking / predator_prey: the variants specified in VARIANTS.md (BASELINE config 5; no reference source, no CPU baseline)")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-steps", type=int, default=200)
     ap.add_argument("--ref-envs", type=int, default=256)
@@ -380,8 +416,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.variant == "flocking":
-        flocking_line(args, torch, rank, world, local_rank, barrier, max_over_ranks)
+    if args.variant != "assembly":
+        (flocking_line if args.variant == "flocking" else predator_prey_line)(args, torch, rank, world, local_rank, barrier, max_over_ranks)
         if world > 1:
             dist.destroy_process_group()
         return

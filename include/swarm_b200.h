@@ -242,6 +242,32 @@ int swarm_is_observed(const swarm_sim *sim);
 int swarm_flock_observe(swarm_sim *sim, void *stream);
 int swarm_flock_step(swarm_sim *sim, const void *act, int act_dtype, void *stream);
 
+/* ---- PredatorPreySwarm variant (VARIANTS.md 4).  Registered by the reference (cus_gym/gym/envs/__init__.py:14-19), no source
+ * shipped: a SPECIFIED variant, parity unpinned.  Stateless calls: the caller owns every buffer (device memory).  Agents
+ * [0, n_p) are pursuers, [n_p, n_p + n_e) escapers, n_p + n_e <= 128.  obs [E][4 * (12 + is_con_self_state)][n]: the assembly head
+ * rows (CPP:102-126) over the 6 nearest agents of the own type, then of the other type; neighbor_index [E][n][12] likewise. */
+enum { SWARM_PP_INPUT = 0, SWARM_PP_STATIC = 1, SWARM_PP_RANDOM = 2, SWARM_PP_NEAREST = 3 };
+typedef struct swarm_pp_config {
+    uint32_t struct_size;
+    int32_t device, num_envs, n_p, n_e;
+    int32_t is_con_self_state, is_periodic, billiards;   /* billiards: elastic walls instead of the wall spring / damper         */
+    int32_t out_dtype;                                   /* SWARM_F32 / SWARM_F64 for obs and reward                             */
+    int32_t strategy_p, strategy_e;                      /* SWARM_PP_*: whose actions come from `act`, who is scripted           */
+    double d_sen, size_a, k_ball, k_wall, c_wall, dt, vel_max_p, vel_max_e, mass;
+    double boundary_pos[4];                              /* x_min, y_max, x_max, y_min like ENV:117                              */
+    uint64_t seed;                                       /* SWARM_PP_RANDOM draws: counter-based on (seed, step_index, env, agent) */
+} swarm_pp_config;
+typedef struct swarm_pp_buffers {
+    uint32_t struct_size;
+    double *p, *dp;                 /* [E][2][n] f64, updated in place by swarm_pp_step                                          */
+    void *obs, *reward;             /* [E][obs_dim][n], [E][n] in out_dtype                                                      */
+    int32_t *neighbor_index;        /* [E][n][12]                                                                                */
+} swarm_pp_buffers;
+int swarm_pp_obs_dim(const swarm_pp_config *cfg);
+int swarm_pp_observe(const swarm_pp_config *cfg, const swarm_pp_buffers *buf, void *stream);
+int swarm_pp_step(const swarm_pp_config *cfg, const swarm_pp_buffers *buf, const void *act, int act_dtype, uint64_t step_index,
+                  void *stream);
+
 /* reset() tail, ENV:221 -> _get_obs: observation (+ reward) of the current state, no dynamics. */
 int swarm_observe(swarm_sim *sim, void *stream);
 

@@ -39,13 +39,32 @@ class SwarmBuffers(C.Structure):
     ]
 
 
+SWARM_PP_INPUT, SWARM_PP_STATIC, SWARM_PP_RANDOM, SWARM_PP_NEAREST = 0, 1, 2, 3
+
+
+class SwarmPPConfig(C.Structure):          # swarm_pp_config (include/swarm_b200.h)
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("num_envs", C.c_int32), ("n_p", C.c_int32), ("n_e", C.c_int32),
+        ("is_con_self_state", C.c_int32), ("is_periodic", C.c_int32), ("billiards", C.c_int32), ("out_dtype", C.c_int32),
+        ("strategy_p", C.c_int32), ("strategy_e", C.c_int32),
+        ("d_sen", C.c_double), ("size_a", C.c_double), ("k_ball", C.c_double), ("k_wall", C.c_double), ("c_wall", C.c_double),
+        ("dt", C.c_double), ("vel_max_p", C.c_double), ("vel_max_e", C.c_double), ("mass", C.c_double),
+        ("boundary_pos", C.c_double * 4), ("seed", C.c_uint64),
+    ]
+
+
+class SwarmPPBuffers(C.Structure):         # swarm_pp_buffers
+    _fields_ = [("struct_size", C.c_uint32), ("p", C.c_void_p), ("dp", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p),
+                ("neighbor_index", C.c_void_p)]
+
+
 # every symbol include/swarm_b200.h declares (tests check the library exports all of them)
 LEGACY_SYMBOLS = ["_get_observation", "_get_reward", "_sf_b2b_all", "_get_dist_b2w", "calculateActionPrior"]
 BATCHED_SYMBOLS = ["swarm_grid_pad", "swarm_obs_dim", "swarm_create", "swarm_destroy", "swarm_set_grid",
                    "swarm_set_shapes", "swarm_reset", "swarm_metrics", "swarm_set_obs_buffer", "swarm_strategy_actions",
                    "swarm_mark_state_dirty", "swarm_observe", "swarm_step", "swarm_step_host", "swarm_a_prior_ptr",
                    "swarm_fill_actions", "swarm_launch_count", "swarm_kernel_geometry", "swarm_last_error",
-                   "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho", "swarm_restore_observation", "swarm_is_observed", "swarm_reset_envs", "swarm_measure_fma_peak", "swarm_fast_path", "swarm_set_grid_pose", "swarm_flock_observe", "swarm_flock_step", "swarm_selftest_division"]
+                   "swarm_abi_version", "swarm_sqrt_threshold", "swarm_debug_rho", "swarm_restore_observation", "swarm_is_observed", "swarm_reset_envs", "swarm_measure_fma_peak", "swarm_fast_path", "swarm_set_grid_pose", "swarm_flock_observe", "swarm_flock_step", "swarm_selftest_division", "swarm_pp_obs_dim", "swarm_pp_observe", "swarm_pp_step"]
 ROLLOUT_SYMBOLS = ["swarm_rollout_push", "swarm_rollout_gather", "swarm_rollout_push_parts", "swarm_rollout_gather_ring"]
 SWARM_PUSH_OBS, SWARM_PUSH_NEXT_OBS, SWARM_PUSH_SMALL = 1, 2, 4
 POLICY_SYMBOLS = ["swarm_policy_create", "swarm_policy_destroy", "swarm_policy_load", "swarm_policy_step", "swarm_policy_launch_count",
@@ -126,6 +145,9 @@ def load():
     lib.swarm_policy_launch_count.restype = C.c_int64
     lib.swarm_policy_launch_count.argtypes = [C.c_void_p]
     lib.swarm_debug_rho.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+    lib.swarm_pp_obs_dim.argtypes = [C.POINTER(SwarmPPConfig)]
+    lib.swarm_pp_observe.argtypes = [C.POINTER(SwarmPPConfig), C.POINTER(SwarmPPBuffers), C.c_void_p]
+    lib.swarm_pp_step.argtypes = [C.POINTER(SwarmPPConfig), C.POINTER(SwarmPPBuffers), C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p]
     lib.swarm_selftest_division.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, C.POINTER(C.c_uint64)]
     lib.swarm_sqrt_threshold.restype = C.c_double
     lib.swarm_sqrt_threshold.argtypes = [C.c_double, C.c_int]

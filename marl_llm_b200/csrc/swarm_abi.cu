@@ -781,6 +781,48 @@ static int flock_launch(swarm_sim *s, bool dyn, const void *act, int act_dtype, 
     return SWARM_OK;
 }
 
+/* ---- predator-prey variant (stateless; VARIANTS.md 4) ---- */
+int swarm_pp_obs_dim(const swarm_pp_config *c) {
+    if (!c || c->struct_size != sizeof(swarm_pp_config)) return -1;
+    return 4 * (2 * TOPO + (c->is_con_self_state ? 1 : 0));
+}
+static int pp_launch(const swarm_pp_config *c, const swarm_pp_buffers *b, bool dyn, const void *act, int act_dtype, uint64_t step,
+                     cudaStream_t st) {
+    if (!c || !b || c->struct_size != sizeof(swarm_pp_config) || b->struct_size != sizeof(swarm_pp_buffers))
+        return fail(SWARM_ERR_INVALID, "swarm_pp: bad config / buffers (struct_size)");
+    const int n = c->n_p + c->n_e;
+    if (c->num_envs < 1 || c->n_p < 0 || c->n_e < 0 || n < 1 || n > 128) return fail(SWARM_ERR_UNSUPPORTED, "swarm_pp: 1 <= n_p + n_e <= 128");
+    if (!b->p || !b->dp || !b->obs || !b->reward || !b->neighbor_index) return fail(SWARM_ERR_INVALID, "swarm_pp: null buffer");
+    if (c->out_dtype != SWARM_F32 && c->out_dtype != SWARM_F64) return fail(SWARM_ERR_INVALID, "swarm_pp: out_dtype");
+    for (int sgy : {c->strategy_p, c->strategy_e}) if (sgy < 0 || sgy > 3) return fail(SWARM_ERR_INVALID, "swarm_pp: strategy");
+    if (dyn && (c->strategy_p == SWARM_PP_INPUT || c->strategy_e == SWARM_PP_INPUT) && !act) return fail(SWARM_ERR_INVALID, "swarm_pp: null actions");
+    if (!(c->d_sen > 0) || !(c->size_a > 0) || !(c->dt > 0) || !(c->mass > 0)) return fail(SWARM_ERR_INVALID, "swarm_pp: d_sen, size_a, dt, mass must be positive");
+    CU_TRY(cudaSetDevice(c->device));
+    PPParams Q{};
+    Q.n_p = c->n_p; Q.n_e = c->n_e; Q.self_state = c->is_con_self_state; Q.periodic = c->is_periodic; Q.billiards = c->billiards;
+    Q.strat_p = c->strategy_p; Q.strat_e = c->strategy_e; Q.act_f32 = (act_dtype == SWARM_F32);
+    Q.two_size = c->size_a + c->size_a; Q.size_a = c->size_a;
+    Q.T_sen = thresh_lt(c->d_sen); Q.T_col = thresh_lt(Q.two_size);
+    Q.k_ball = c->k_ball; Q.k_wall = c->k_wall; Q.c_wall = c->c_wall; Q.dt = c->dt; Q.vmax_p = c->vel_max_p; Q.vmax_e = c->vel_max_e; Q.mass = c->mass;
+    Q.bx_min = c->boundary_pos[0]; Q.by_max = c->boundary_pos[1]; Q.bx_max = c->boundary_pos[2]; Q.by_min = c->boundary_pos[3];
+    Q.half_w = (Q.bx_max - Q.bx_min) / 2.0; Q.half_h = (Q.by_max - Q.by_min) / 2.0;
+    Q.p = b->p; Q.dp = b->dp; Q.act = act; Q.obs = b->obs; Q.reward = b->reward; Q.nbr = b->neighbor_index;
+    Q.seed = c->seed; Q.step = step;
+    const int nt = round32(n);
+    const bool f32 = c->out_dtype == SWARM_F32;
+    if (dyn) { if (f32) k_pp_step<float, true><<<c->num_envs, nt, 0, st>>>(Q); else k_pp_step<double, true><<<c->num_envs, nt, 0, st>>>(Q); }
+    else { if (f32) k_pp_step<float, false><<<c->num_envs, nt, 0, st>>>(Q); else k_pp_step<double, false><<<c->num_envs, nt, 0, st>>>(Q); }
+    CU_TRY(cudaGetLastError());
+    return SWARM_OK;
+}
+int swarm_pp_observe(const swarm_pp_config *c, const swarm_pp_buffers *b, void *stream) {
+    return pp_launch(c, b, false, nullptr, SWARM_F32, 0, (cudaStream_t)stream);
+}
+int swarm_pp_step(const swarm_pp_config *c, const swarm_pp_buffers *b, const void *act, int act_dtype, uint64_t step_index, void *stream) {
+    if (act_dtype != SWARM_F32 && act_dtype != SWARM_F64) return fail(SWARM_ERR_INVALID, "swarm_pp: act_dtype");
+    return pp_launch(c, b, true, act, act_dtype, step_index, (cudaStream_t)stream);
+}
+
 int swarm_flock_observe(swarm_sim *s, void *stream) {
     if (!s) return fail(SWARM_ERR_INVALID, "null handle");
     return flock_launch(s, false, nullptr, SWARM_F32, (cudaStream_t)stream);

@@ -7,6 +7,6 @@ while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -shared -Xcompiler -fPIC $flags \
        -Xptxas -v -o marl_llm_b200/lib/variants/$name.so marl_llm_b200/csrc/swarm_abi.cu marl_llm_b200/csrc/rollout_abi.cu marl_llm_b200/csrc/policy_abi.cu 2>&1 \
-       | grep -A2 "k_stepIfLb1ELb0ELi128ELi[12]" | grep -E "Used" | sed "s/^/[$name] /" &
+       | grep -c "Used" | sed "s/^/[$name] kernels: /" &
 done
 wait
