@@ -12,7 +12,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
         "sm__cycles_elapsed.avg", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
-        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__inst_executed.avg.per_cycle_active",
+        "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed"]
 res = []
 for v in r[2:]:
     d = {"_kernel": v[h.index("Kernel Name")]}
