@@ -56,6 +56,8 @@ constexpr bool vel_global = false;
 #endif
 size_t step_smem_bytes(int nt, int n_g_pad, int n_words, bool emit, int n_obs, int phase = 0, int rec_cap = -1, int lat_n = 0) {
     (void)n_g_pad;
+    if (phase == 1)      // first half: state tile + 2 mbarrier slots (unused) + neighbour list + filter positions (k_step: SLIM)
+        return (size_t)4 * nt * sizeof(double) + 16 + (size_t)TOPO * nt * sizeof(int) + (size_t)nt * sizeof(float2);
     size_t ring = (size_t)2 * CHUNK_CELLS * sizeof(double2);
     if (rec_cap >= 0) ring = std::max(ring, (size_t)(nt / 32) * ((size_t)4 * rec_cap + 128 + 16));      // lookup scan: per warp, row records + running counts
     size_t b = ring + (rec_cap >= 0 ? 0 : (size_t)n_words * sizeof(float4)) + (size_t)(vel_global && phase == 2 ? 2 : 4) * nt * sizeof(double);   // TMA ring / records + word boxes + state tile
@@ -168,6 +170,7 @@ struct swarm_sim {
     KParams K;
     int nt;                 // threads per CTA
     bool split;             // step = two launches (k_step PH 1 + PH 2)
+    size_t smem1;           // dynamic shared memory of the first half
     size_t smem;            // dynamic shared memory of k_step PH 0 / 1
     size_t smem2;           // ... of the second-half kernel (PH 2)
     int pending;            // a_prior buffer holding the prior of the CURRENT state
@@ -257,6 +260,7 @@ int swarm_create(const swarm_config *cfg, const swarm_buffers *buf, swarm_sim **
     s->nt = round32(cfg->n_a);
     s->smem = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max);
     s->smem2 = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max, 2);
+    s->smem1 = step_smem_bytes(s->nt, K.n_g_pad, K.n_words, cfg->emit_indices != 0, cfg->num_obs_grid_max, 1);
     if (const char *x = getenv("SWARM_DEBUG_EXTRA_SMEM")) s->smem += (size_t)atoi(x);   // occupancy experiments only
     if (s->smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete s;
@@ -744,13 +748,13 @@ static int launch_step(swarm_sim *s, bool dyn, const void *act, int act_dtype, c
                 K.env0 = c * per;
                 const int n = std::min(per, ctas - K.env0);
                 if (n <= 0) break;
-                k1<<<n, s->nt, s->smem, s->side[c & 1]>>>(K);
+                k1<<<n, s->nt, s->smem1, s->side[c & 1]>>>(K);
                 k2<<<n, s->nt, sm2, s->side[c & 1]>>>(K);
                 s->launches += 2;
             }
             for (int k = 0; k < 2; ++k) { CU_TRY(cudaEventRecord(s->ev_join[k], s->side[k])); CU_TRY(cudaStreamWaitEvent(st, s->ev_join[k], 0)); }
         } else {
-            k1<<<ctas, s->nt, s->smem, st>>>(K);
+            k1<<<ctas, s->nt, s->smem1, st>>>(K);
             k2<<<ctas, s->nt, sm2, st>>>(K);
             s->launches += 2;
         }
@@ -770,8 +774,7 @@ static int flock_launch(swarm_sim *s, bool dyn, const void *act, int act_dtype, 
     K.act = act; K.act_f32 = (act_dtype == SWARM_F32);
     const bool f32 = s->cfg.out_dtype == SWARM_F32;
     step_fn_t k1 = s->nt == 32 ? pick_step(f32, dyn, false, 32, 1) : pick_first_half_wide(f32, dyn);   // the assembly step's first half, unchanged
-    CU_TRY(raise_smem_limit((const void *)k1, s->smem));
-    k1<<<s->cfg.num_envs, s->nt, s->smem, st>>>(K);
+    k1<<<s->cfg.num_envs, s->nt, s->smem1, st>>>(K);
     const double d_ref = 2.0 * s->cfg.r_avoid;
     if (f32) k_flock_reward<float><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (float *)s->buf.reward);
     else k_flock_reward<double><<<s->cfg.num_envs, s->nt, 0, st>>>(s->cfg.n_a, K.p, K.dp, K.nbr, K.T_avoid, d_ref, 1.0, 0.5, 0.5, K.periodic, K.half_w, K.half_h, (double *)s->buf.reward);
