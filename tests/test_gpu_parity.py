@@ -397,7 +397,8 @@ def test_lookup_scan_equals_culled_scan_at_scale():
 
 def synthetic_shapes():
     """Lattice shapes that stress the lookup tables: a ring (an agent at its centre has dozens of equidistant nearest cells ->
-    spilled candidate lists), scattered dots (holes inside rows), one long row, a 2-cell shape, a wide block (40 columns)."""
+    spilled candidate lists), scattered dots (holes inside rows), one long row, a 2-cell shape, a wide block (40 columns), a disc,
+    denser dots, a tall block, an L, a small ring."""
     L = 0.06
     def cells(mask):
         iy, ix = np.nonzero(mask)                                  # row-major order = the numbering of assembly_cfg.py:60-79
@@ -408,6 +409,9 @@ def synthetic_shapes():
     rng = np.random.RandomState(0)
     out = [cells((r > 11.5) & (r < 13.5)), cells(rng.rand(30, 30) < 0.25), cells(np.ones((1, 50), bool)),
            cells(np.array([[1, 0, 0, 1]], bool)), cells(np.ones((12, 40), bool))]
+    # ten shapes in all: the kernels read the first eight tables from their parameters and the rest from global memory
+    ell = np.zeros((24, 24), bool); ell[:, :5] = True; ell[-5:, :] = True
+    out += [cells(r < 9.5), cells(rng.rand(20, 44) < 0.5), cells(np.ones((40, 12), bool)), cells(ell), cells((r > 5.5) & (r < 8.5))]
     return out, [L] * len(out)
 
 
