@@ -415,13 +415,36 @@ def synthetic_shapes():
     return out, [L] * len(out)
 
 
+def fine_shapes():
+    """A fine lattice (l_cell = 0.03: the sensing disc spans 27 rows and ~560 cells): 32 row lanes per agent, more than 255
+    candidates per agent (the provisional-slot field of a row record saturates), every agent in range senses more than 80 cells."""
+    L = 0.03
+    def cells(mask):
+        iy, ix = np.nonzero(mask)
+        pts = np.stack([ix * L, iy * L]).astype(np.float64)
+        return np.ascontiguousarray(pts - pts.mean(axis=1, keepdims=True))
+    yy, xx = np.mgrid[0:40, 0:40]
+    r = np.hypot(xx - 19.5, yy - 19.5)
+    out = [cells(np.ones((30, 30), bool)), cells((r > 9) & (r < 19.5)), cells(np.ones((16, 60), bool))]
+    return out, [L] * len(out)
+
+
 @pytest.mark.parametrize("n_a", [30, 64])
 def test_lookup_scan_on_synthetic_lattice_shapes(n_a):
     """The lookup scan against the oracle on a shape library built to stress its tables (see synthetic_shapes): poses through
     set_grid (detected) and set_grid_pose (exact), agents spawned inside, on the rim and around each shape."""
-    from marl_llm_b200.batched import BatchedAssemblySim
     origins, l_cells = synthetic_shapes()
-    E = 40
+    run_synthetic_library(origins, l_cells, n_a, E=40, steps=40, min_sensed=1000)
+
+
+def test_lookup_scan_on_a_fine_lattice():
+    """l_cell = 0.03 (see fine_shapes): 32 row lanes per agent, saturated provisional slots, subsampled lists outside the shape."""
+    origins, l_cells = fine_shapes()
+    run_synthetic_library(origins, l_cells, 30, E=12, steps=15, min_sensed=5000)
+
+
+def run_synthetic_library(origins, l_cells, n_a, E, steps, min_sensed):
+    from marl_llm_b200.batched import BatchedAssemblySim
     ngm = max(o.shape[1] for o in origins)
     r_avoid = 0.2
     rng = np.random.RandomState(n_a)
@@ -458,13 +481,13 @@ def test_lookup_scan_on_synthetic_lattice_shapes(n_a):
     ob.observe(with_reward=True)
     for s_ in sims:
         compare_all(s_, ob, -1, fields=("obs", "reward", "nbr", "in_flags", "sensed", "occupied"))
-    for t in range(40):
+    for t in range(steps):
         a = goal_seeking_action(ob.obs, ob.dp, rng)
         ob.step(a)
         for s_ in sims:
             s_.step(torch.from_numpy(a).cuda())
             compare_all(s_, ob, t)
-    assert ob.in_flags.sum() > 0 and (ob.sensed_index >= 0).sum() > 1000
+    assert ob.in_flags.sum() > 0 and (ob.sensed_index >= 0).sum() > min_sensed
 
 
 def test_agents_far_outside_the_arena_take_the_literal_scan():
