@@ -414,7 +414,9 @@ int swarm_set_shapes(swarm_sim *s, int32_t n_shapes, const double *grids, const 
     double l_min = l_cell[0];
     for (int k = 1; k < n_shapes; ++k) l_min = std::min(l_min, l_cell[k]);
     const double rr = s->cfg.d_sen / l_min;
+    // (the lookup scan finds covered cells among an agent's sensing candidates: the covering radius must be the smaller one)
     const bool eligible = ((s->split && s->nt == 32) || (!s->split && s->nt > 32)) && s->K.n_words <= 32 && ngm <= 1023 && rr <= 14.9 && !s->cfg.brute_force_scan &&
+                          0.5 * s->cfg.r_avoid + 1e-6 < s->cfg.d_sen &&
                           !getenv("SWARM_NO_LOOKUP_SCAN") && !(s->nt > 32 && getenv("SWARM_NO_LOOKUP_SCAN_BIG"));
     if (!eligible) return SWARM_OK;
     const double half_extent = std::max(s->K.half_w, s->K.half_h);
