@@ -37,7 +37,8 @@ def make_sim(E, n_a, n_g_max, r_avoid, **kw):
         sim.set_shapes(shapes["grid_origin"], shapes["l_cell"])
     import os
     big_fits = not (kw.get("emit_indices", False) and n_a > 512)     # 1024 agents + index arrays: shared memory is full without the records
-    sim.expect_fast = lookup and big_fits and not kw.get("brute_force_scan", False) and not (n_a <= 32 and os.environ.get("SWARM_FUSED_STEP"))
+    radii_ok = 0.5 * r_avoid + 1e-6 < kw.get("d_sen", 0.4)          # covered cells are looked for among the sensing candidates
+    sim.expect_fast = lookup and big_fits and radii_ok and not kw.get("brute_force_scan", False) and not (n_a <= 32 and os.environ.get("SWARM_FUSED_STEP"))
     return sim
 
 
